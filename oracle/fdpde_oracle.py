@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front end of the CPU oracle (oracle/fdpde_oracle.c).
+
+Mirrors the reference's ``Inpainter(**options).inpaint(image, mask)`` surface
+(/root/reference/heightmap_interpolation/inpainting/fd_pde_inpainter.py:52-185) closely enough
+for parity tests to read like the reference's own usage.  Parity status: PINNED by
+tests/test_oracle_golden.py against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).
+
+Only tests/, ``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may import this
+module.  The product package ``heightmap_interpolation_b200`` never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libfdpde_oracle.so")
+
+METHODS = {"harmonic": 0, "sobolev": 0, "ccst": 1, "tv": 2, "amle": 3}
+# convolver name -> (orientation, border, masked)       convolver.py:47-69, SURVEY.md A.2
+CONVOLVERS = {
+    "opencv": (+1, 0, 0),
+    "masked": (-1, 0, 1),
+    "masked-parallel": (-1, 0, 1),
+    # convolver.py:17-18 maps "scipy-ndimage" to ScipySignalConvolver (zero padding); the
+    # symmetric-border ScipyNDImageConvolver (:52-54) is unreachable by name.
+    "scipy-ndimage": (-1, 2, 0),
+    "scipy-signal": (-1, 2, 0),
+}
+CRITERIA = {"relative": 0, "absolute": 1, "absolute_percent": 2}
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [
+        ("method", ctypes.c_int),
+        ("orientation", ctypes.c_int),
+        ("border", ctypes.c_int),
+        ("masked", ctypes.c_int),
+        ("criteria", ctypes.c_int),
+        ("reserved", ctypes.c_int),
+        ("dt", ctypes.c_double),
+        ("tension", ctypes.c_double),
+        ("epsilon", ctypes.c_double),
+        ("relaxation", ctypes.c_double),
+        ("term_thres", ctypes.c_double),
+        ("term_check_iters", ctypes.c_longlong),
+        ("max_iters", ctypes.c_longlong),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle with gcc (building the checker is not using it)."""
+    src = [os.path.join(_HERE, f) for f in ("fdpde_oracle.c", "fdpde_oracle_impl.h", "fdpde_oracle.h")]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        for suf in ("f64", "f32"):
+            g = getattr(L, "oracle_inpaint_grid_" + suf)
+            g.restype = ctypes.c_int
+            g.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                          ctypes.POINTER(_Params), ctypes.c_void_p,
+                          ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double),
+                          ctypes.POINTER(ctypes.c_int)]
+            s = getattr(L, "oracle_step_fun_" + suf)
+            s.restype = ctypes.c_int
+            s.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                          ctypes.POINTER(_Params), ctypes.c_void_p]
+        L.oracle_dilate3x3.restype = None
+        L.oracle_dilate3x3.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        _lib = L
+    return _lib
+
+
+def _suffix(a):
+    if a.dtype == np.float64:
+        return "f64"
+    if a.dtype == np.float32:
+        return "f32"
+    raise TypeError("oracle supports float32/float64 grids, got %s" % a.dtype)
+
+
+class OracleInpainter:
+    """CPU oracle with the reference's constructor options."""
+
+    def __init__(self, method, **kwargs):
+        self.method = method.lower()
+        if self.method not in METHODS:
+            raise ValueError("unknown method " + method)
+        self.dt = kwargs.pop("update_step_size", 0.01)
+        self.term_check_iters = kwargs.pop("term_check_iters", 1000)
+        self.term_thres = kwargs.pop("term_thres", 1e-8)
+        self.max_iters = int(kwargs.pop("max_iters", 1e8))
+        self.relaxation = kwargs.pop("relaxation", 0)
+        self.init_with = kwargs.pop("init_with", "zeros")
+        self.convolver_type = kwargs.pop("convolver", "masked")
+        self.term_criteria = kwargs.pop("term_criteria", "relative")
+        self.tension = kwargs.pop("tension", 0.0)
+        self.epsilon = kwargs.pop("epsilon", 1e-2)
+        if self.convolver_type.lower() not in CONVOLVERS:
+            raise ValueError("Unknown convolver type '{:s}'".format(self.convolver_type))
+        # results of the last solve (the reference only prints these)
+        self.updates_done = None
+        self.last_diff = None
+        self.converged = None
+
+    def _params(self, term_thres, max_iters=None):
+        o, b, m = CONVOLVERS[self.convolver_type.lower()]
+        crit = CRITERIA.get(self.term_criteria, -1)
+        if crit < 0:
+            raise ValueError("Unknown termination criteria!")
+        return _Params(METHODS[self.method], o, b, m, 0 if crit == 0 else 1, 0,
+                       float(self.dt), float(self.tension), float(self.epsilon),
+                       float(self.relaxation), float(term_thres),
+                       int(self.term_check_iters), int(self.max_iters if max_iters is None else max_iters))
+
+    def initialize(self, image, mask):
+        """initializer.py:14-18 — in place on the caller's array, zeros/mean only."""
+        if self.init_with == "zeros":
+            image[~mask] = 0
+        elif self.init_with == "mean":
+            image[~mask] = np.mean(image[mask])
+        else:
+            raise ValueError("oracle supports init_with zeros/mean only")
+        return image
+
+    def step_fun(self, f, work_mask=None):
+        f = np.ascontiguousarray(f)
+        suf = _suffix(f)
+        out = np.empty_like(f)
+        wm = None
+        if work_mask is not None:
+            wm = np.ascontiguousarray(work_mask, dtype=np.uint8)
+        p = self._params(self.term_thres)
+        rc = getattr(lib(), "oracle_step_fun_" + suf)(
+            f.ctypes.data, None if wm is None else wm.ctypes.data, f.shape[0], f.shape[1],
+            ctypes.byref(p), out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("oracle_step_fun failed rc=%d" % rc)
+        return out
+
+    def inpaint_grid(self, image, mask):
+        image = np.ascontiguousarray(image)
+        suf = _suffix(image)
+        m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+        thres = self.term_thres
+        if self.term_criteria == "absolute_percent":      # fd_pde_inpainter.py:149-155 (mutates self)
+            z_range = abs(np.max(image) - np.min(image))    # stays in the grid dtype, like NumPy does
+            self.term_thres = z_range * self.term_thres
+            thres = self.term_thres
+        p = self._params(thres)
+        out = np.empty_like(image)
+        done = ctypes.c_longlong(0)
+        diff = ctypes.c_double(0)
+        conv = ctypes.c_int(0)
+        rc = getattr(lib(), "oracle_inpaint_grid_" + suf)(
+            image.ctypes.data, m8.ctypes.data, image.shape[0], image.shape[1], ctypes.byref(p),
+            out.ctypes.data, ctypes.byref(done), ctypes.byref(diff), ctypes.byref(conv))
+        if rc != 0:
+            raise RuntimeError("oracle_inpaint_grid failed rc=%d" % rc)
+        self.updates_done, self.last_diff, self.converged = done.value, diff.value, bool(conv.value)
+        return out
+
+    def inpaint(self, image, mask):
+        image = self.initialize(image, mask)
+        return self.inpaint_grid(image, mask)
+
+
+def dilate3x3(unknown):
+    u = np.ascontiguousarray(unknown, dtype=np.uint8)
+    out = np.empty_like(u)
+    lib().oracle_dilate3x3(u.ctypes.data, out.ctypes.data, u.shape[0], u.shape[1])
+    return out

@@ -1,0 +1,94 @@
+"""The CPU oracle (oracle/) against fixtures produced by the unmodified reference.
+
+This is what pins the oracle: every later CUDA parity test compares
+against the oracle, so the oracle itself must reproduce the reference's outputs first.
+"""
+import numpy as np
+import pytest
+
+from helpers import DTYPES, METHOD_OPTS, parse_converged_meta, range_err
+from oracle.fdpde_oracle import OracleInpainter
+
+METHODS = ["harmonic", "ccst", "tv", "amle"]
+# f64: the oracle and the reference differ only by summation order inside a 3x3 sum.
+ORACLE_TOL = {"f64": 1e-12, "f32": 2e-6}
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("conv", ["opencv", "masked", "scipy-ndimage", "scipy-signal"])
+@pytest.mark.parametrize("method", METHODS)
+def test_step_fun_matches_reference(golden_step, method, conv, dt):
+    f = golden_step["field"].astype(DTYPES[dt])
+    ref = golden_step["step__%s__%s__%s" % (method, conv, dt)]
+    work = np.ones(f.shape, dtype=np.uint8) if conv.startswith("masked") else None
+    got = OracleInpainter(method, convolver=conv, **METHOD_OPTS[method]).step_fun(f, work)
+    if not conv.startswith("scipy"):   # scipy.signal.convolve promotes f32 x f64-kernel to f64
+        assert got.dtype == ref.dtype
+    assert range_err(got, ref) <= ORACLE_TOL[dt]
+
+
+@pytest.mark.parametrize("K", [1, 10, 60])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("conv", ["opencv", "masked"])
+@pytest.mark.parametrize("method", METHODS)
+def test_k_sweeps_match_reference(golden_sweeps, method, conv, dt, K):
+    img = golden_sweeps["image__" + dt].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__%s__%s__%s__%d" % (method, conv, dt, K)]
+    o = OracleInpainter(method, convolver=conv, max_iters=K, term_thres=1e-300,
+                        term_check_iters=10 ** 9, **METHOD_OPTS[method])
+    got = o.inpaint(img, mask)
+    assert o.updates_done == K and not o.converged
+    assert np.array_equal(got[mask], ref[mask])          # known cells bit-exact
+    assert range_err(got, ref) <= ORACLE_TOL[dt] * max(1, K // 10)
+
+
+@pytest.mark.parametrize("conv", ["scipy-ndimage", "scipy-signal"])
+@pytest.mark.parametrize("method", METHODS)
+def test_other_border_rules(golden_sweeps, method, conv):
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__%s__%s__f64__10" % (method, conv)]
+    o = OracleInpainter(method, convolver=conv, max_iters=10, term_thres=1e-300,
+                        term_check_iters=10 ** 9, **METHOD_OPTS[method])
+    assert range_err(o.inpaint(img, mask), ref) <= 1e-12
+
+
+@pytest.mark.parametrize("t", [0, 1])
+def test_ccst_tension_end_points(golden_sweeps, t):
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__ccst_t%d__opencv__f64__10" % t]
+    o = OracleInpainter("ccst", convolver="opencv", max_iters=10, term_thres=1e-300,
+                        term_check_iters=10 ** 9, update_step_size=0.01, tension=float(t))
+    assert range_err(o.inpaint(img, mask), ref) <= 1e-12
+
+
+def test_over_relaxation_f64(golden_sweeps):
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__harmonic_relax15__opencv__f64__10"]
+    o = OracleInpainter("harmonic", convolver="opencv", max_iters=10, term_thres=1e-300,
+                        term_check_iters=10 ** 9, update_step_size=0.2, relaxation=1.5)
+    got = o.inpaint(img, mask)
+    assert np.array_equal(got[mask], ref[mask])
+    assert range_err(got, ref) <= 1e-12
+
+
+def test_converged_runs_match_reference(golden_converged):
+    mask = golden_converged["mask"]
+    for c in parse_converged_meta(golden_converged):
+        img = golden_converged["image__" + c["dtype"]].copy()
+        opts = dict(METHOD_OPTS[c["method"]])
+        opts.update(convolver=c["convolver"], term_criteria=c["criteria"], term_thres=c["thres"],
+                    term_check_iters=c["T"])
+        opts.update(c["extra"])
+        o = OracleInpainter(c["method"], **opts)
+        got = o.inpaint(img, mask)
+        ref = golden_converged[c["key"]]
+        assert o.updates_done == c["updates"], c
+        assert o.converged == c["converged"], c
+        assert o.last_diff == pytest.approx(c["diff"], rel=1e-3 if c["dtype"] == "f32" else 1e-7), c
+        assert o.term_thres == pytest.approx(c["final_thres"], rel=1e-12), c  # absolute_percent mutation
+        assert np.array_equal(got[mask], ref[mask]), c
+        assert range_err(got, ref) <= (1e-11 if c["dtype"] == "f64" else 5e-6), c
