@@ -1,0 +1,44 @@
+"""Build the CUDA shared library in-tree with nvcc for sm_100a (B200).
+
+``python -m heightmap_interpolation_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
+without a GPU; the resulting ``csrc/libhmi_b200.so`` is git-ignored but travels with the tree.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libhmi_b200.so")
+SOURCES = ["hmi_capi.cu", "hmi_generic.cu", "hmi_stream.cu", "hmi_host.cpp"]
+HEADERS = ["hmi_common.cuh", "hmi_stream.cuh", os.path.join("..", "..", "include", "hmi_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

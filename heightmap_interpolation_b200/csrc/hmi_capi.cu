@@ -1,0 +1,485 @@
+// C ABI of the B200 FD-PDE inpainting solver (see include/hmi_b200.h for the contract and the
+// reference code each entry point replaces).  Host-side orchestration only: buffer ownership,
+// kernel selection, the temporal-block schedule and the reference's check cadence
+// (heightmap_interpolation/inpainting/fd_pde_inpainter.py:311-351).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hmi_common.cuh"
+#include "hmi_stream.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(HMI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct hmi_solver {
+    hmi_params p;
+    int elem = 0;            // bytes per cell
+    int radius = 1;          // stencil radius of one sweep
+    long long pitch = 0;     // elements per row
+    long long mpitch = 0;    // bytes per mask row
+    int phys_rows = 0;       // ghost_top + rows + ghost_bottom
+    char *buf[2] = {nullptr, nullptr};
+    uint8_t *mask = nullptr;
+    int cur = 0;
+    double *d_partials = nullptr;
+    unsigned int *d_counter = nullptr;
+    double *d_result = nullptr;
+    double *h_result = nullptr;  // pinned
+    int max_blocks = 0;
+    bool use_stream = false;
+    int tb = 1;              // sweeps fused per launch
+    int chunk_rows = 0;      // 0 = auto
+    long long launches = 0;
+    bool has_problem = false;
+};
+
+namespace {
+
+template <typename T>
+int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st)
+{
+    const hmi_params &p = s->p;
+    const T *src = reinterpret_cast<const T *>(s->buf[s->cur]) + (long long)p.ghost_top * s->pitch;
+    T *dst = reinterpret_cast<T *>(s->buf[s->cur ^ 1]) + (long long)p.ghost_top * s->pitch;
+    const uint8_t *mask = s->mask + (long long)p.ghost_top * s->mpitch;
+    int nblocks = 0;
+    cudaError_t e;
+    if (s->use_stream) {
+        hmi::StreamArgs<T> a;
+        memset(&a, 0, sizeof(a));
+        a.src = src; a.dst = dst; a.mask = mask;
+        a.pitch = s->pitch; a.mpitch = s->mpitch;
+        a.rows = p.rows; a.cols = p.cols;
+        a.row_lo = lo; a.row_hi = hi;
+        a.read_lo = -p.ghost_top; a.read_hi = p.rows + p.ghost_bottom;
+        a.top_border = p.ghost_top == 0; a.bottom_border = p.ghost_bottom == 0;
+        a.chunk_rows = s->chunk_rows;
+        a.dt = (T)p.dt; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
+        a.do_norm = do_norm ? 1 : 0;
+        a.partials = s->d_partials; a.counter = s->d_counter; a.result = s->d_result;
+        e = hmi::launch_stream<T>(p.method, k, a, st, &nblocks);
+    } else {
+        if (k != 1) return fail(HMI_ERR_STATE, "generic kernel runs one sweep per launch");
+        hmi::SweepArgs<T> a;
+        memset(&a, 0, sizeof(a));
+        a.src = src; a.dst = dst; a.mask = mask;
+        a.pitch = s->pitch; a.mpitch = s->mpitch;
+        a.rows = p.rows; a.cols = p.cols;
+        a.row_lo = lo; a.row_hi = hi;
+        a.top_border = p.ghost_top == 0; a.bottom_border = p.ghost_bottom == 0;
+        a.border = p.border; a.s = p.orientation;
+        a.dt = (T)p.dt; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
+        a.eps2 = (T)(p.epsilon * p.epsilon);
+        a.relax = p.relaxation > 1.0 ? 1 : 0;
+        a.relax_w = (T)p.relaxation; a.one_minus_relax_w = (T)(1.0 - p.relaxation);
+        a.do_norm = do_norm ? 1 : 0;
+        a.partials = s->d_partials; a.counter = s->d_counter; a.result = s->d_result;
+        e = hmi::launch_generic<T>(p.method, a, st, &nblocks);
+    }
+    if (e != cudaSuccess)
+        return fail(HMI_ERR_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(e));
+    if (nblocks > s->max_blocks)
+        return fail(HMI_ERR_STATE, "internal: %d blocks exceed the reduction scratch (%d)", nblocks,
+                    s->max_blocks);
+    s->launches += 1;
+    s->cur ^= 1;
+    return HMI_OK;
+}
+
+int run_block(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st)
+{
+    return s->p.dtype == HMI_F64 ? run_block_t<double>(s, k, lo, hi, do_norm, st)
+                                 : run_block_t<float>(s, k, lo, hi, do_norm, st);
+}
+
+// n sweeps as a sequence of temporal blocks.  On a slab with ghost rows the halos must be fresh
+// on entry and n*radius must not exceed the ghost depth: block j also advances the ghost rows
+// that later blocks of this call still need (a shrinking trapezoid), so no exchange is needed
+// inside the call.
+int do_sweeps(hmi_solver *s, long long n, bool norm_on_last, cudaStream_t st)
+{
+    const hmi_params &p = s->p;
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "hmi_set_problem_* has not been called");
+    if (n < 0) return fail(HMI_ERR_BAD_ARG, "negative sweep count");
+    const bool ghosts = p.ghost_top > 0 || p.ghost_bottom > 0;
+    if (ghosts) {
+        const long long need = n * s->radius;
+        if ((p.ghost_top > 0 && need > p.ghost_top) || (p.ghost_bottom > 0 && need > p.ghost_bottom))
+            return fail(HMI_ERR_BAD_ARG,
+                        "%lld sweeps of radius %d need %lld ghost rows, the slab has %d/%d", n,
+                        s->radius, need, p.ghost_top, p.ghost_bottom);
+    }
+    long long done = 0;
+    while (done < n) {
+        long long k = n - done;
+        if (k > s->tb) k = s->tb;
+        const long long after = n - (done + k);  // sweeps still to run after this block
+        const int lo = p.ghost_top > 0 ? (int)(-after * s->radius) : 0;
+        const int hi = p.rows + (p.ghost_bottom > 0 ? (int)(after * s->radius) : 0);
+        const bool last = (done + k == n);
+        const int rc = run_block(s, (int)k, lo, hi, norm_on_last && last, st);
+        if (rc != HMI_OK) return rc;
+        done += k;
+    }
+    return HMI_OK;
+}
+
+int fetch_norm(hmi_solver *s, cudaStream_t st, hmi_norm *out)
+{
+    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    out->sum_d2 = s->h_result[0];
+    out->sum_f2 = s->h_result[1];
+    out->max_abs = s->h_result[2];
+    out->has_nan = s->h_result[3];
+    return HMI_OK;
+}
+
+double norm_to_diff(const hmi_params &p, const hmi_norm &n)
+{
+    if (p.criteria == HMI_RELATIVE) return sqrt(n.sum_d2) / sqrt(n.sum_f2);  // 0/0 -> NaN like NumPy
+    return n.has_nan != 0.0 ? nan("") : n.max_abs;
+}
+
+void destroy(hmi_solver *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->p.device);
+    cudaFree(s->buf[0]);
+    cudaFree(s->buf[1]);
+    cudaFree(s->mask);
+    cudaFree(s->d_partials);
+    cudaFree(s->d_counter);
+    cudaFree(s->d_result);
+    if (s->h_result) cudaFreeHost(s->h_result);
+    delete s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hmi_abi_version(void) { return HMI_ABI_VERSION; }
+
+const char *hmi_last_error(void) { return g_err; }
+
+int hmi_device_count(void)
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HMI_ERR_NO_DEVICE, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int hmi_create(const hmi_params *params, hmi_solver **out)
+{
+    if (!params || !out) return fail(HMI_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (params->struct_size != (int32_t)sizeof(hmi_params))
+        return fail(HMI_ERR_BAD_ARG, "hmi_params size mismatch: caller %d, library %d",
+                    params->struct_size, (int)sizeof(hmi_params));
+    const hmi_params &p = *params;
+    if (p.rows < 2 || p.cols < 2) return fail(HMI_ERR_BAD_ARG, "grid must be at least 2x2");
+    if (p.dtype != HMI_F32 && p.dtype != HMI_F64) return fail(HMI_ERR_BAD_ARG, "bad dtype");
+    if (p.method < HMI_HARMONIC || p.method > HMI_AMLE) return fail(HMI_ERR_BAD_ARG, "bad method");
+    if (p.orientation != 1 && p.orientation != -1) return fail(HMI_ERR_BAD_ARG, "orientation must be +1/-1");
+    if (p.border < HMI_BORDER_REFLECT101 || p.border > HMI_BORDER_ZERO) return fail(HMI_ERR_BAD_ARG, "bad border");
+    if (p.criteria != HMI_RELATIVE && p.criteria != HMI_ABSOLUTE) return fail(HMI_ERR_BAD_ARG, "bad criteria");
+    if (!(p.dt > 0.0)) return fail(HMI_ERR_BAD_ARG, "update_step_size must be larger than zero");
+    if (!(p.term_thres > 0.0)) return fail(HMI_ERR_BAD_ARG, "term_thres must be larger than zero");
+    if (p.max_iters <= 0) return fail(HMI_ERR_BAD_ARG, "max_iters must be larger than zero");
+    if (p.term_check_iters <= 0) return fail(HMI_ERR_BAD_ARG, "term_check_iters must be larger than zero");
+    if (p.relaxation != 0.0 && (p.relaxation < 1.0 || p.relaxation > 2.0))
+        return fail(HMI_ERR_BAD_ARG, "relaxation must be a number between 1 and 2 (0 to deactivate)");
+    if (p.method == HMI_CCST && (p.tension < 0.0 || p.tension > 1.0))
+        return fail(HMI_ERR_BAD_ARG, "tension parameter must be a number between 0 and 1 (included)");
+    if (p.method == HMI_TV && !(p.epsilon > 0.0)) return fail(HMI_ERR_BAD_ARG, "epsilon must be larger than zero");
+    if (p.ghost_top < 0 || p.ghost_bottom < 0) return fail(HMI_ERR_BAD_ARG, "negative ghost rows");
+    if (p.temporal_block < 0) return fail(HMI_ERR_BAD_ARG, "negative temporal_block");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(HMI_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (p.device < 0 || p.device >= ndev) return fail(HMI_ERR_BAD_ARG, "device %d out of range (%d devices)", p.device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, p.device));
+    if (prop.major != 10)
+        return fail(HMI_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    p.device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(p.device));
+
+    hmi_solver *s = new (std::nothrow) hmi_solver();
+    if (!s) return fail(HMI_ERR_CUDA, "out of host memory");
+    s->p = p;
+    s->elem = p.dtype == HMI_F64 ? 8 : 4;
+    s->radius = hmi::method_radius(p.method);
+    s->pitch = round_up(p.cols, 32);
+    s->mpitch = round_up(p.cols, 128);
+    s->phys_rows = p.ghost_top + p.rows + p.ghost_bottom;
+
+    // kernel selection
+    const bool stream_ok = (p.method == HMI_HARMONIC || p.method == HMI_CCST) &&
+                           p.border == HMI_BORDER_REFLECT101 && !(p.relaxation > 1.0);
+    int tb = 1;
+    bool use_stream = false;
+    if (p.kernel == HMI_KERNEL_STREAM && !stream_ok) {
+        delete s;
+        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel covers harmonic/ccst with reflect-101 borders and no over-relaxation");
+    }
+    if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
+        const int maxk = hmi::stream_max_k(p.method, p.dtype);
+        tb = p.temporal_block > 0 ? p.temporal_block : (p.method == HMI_CCST ? 2 : 4);
+        if (tb > maxk) tb = maxk;
+        // the mirrored ghost loads need the mirror cell to exist: shrink the block on small grids
+        const int min_dim = p.cols < p.rows ? p.cols : p.rows;
+        while (tb > 1 && 2 * hmi::stream_halo(p.method, tb) + 2 > min_dim) --tb;
+        use_stream = 2 * hmi::stream_halo(p.method, tb) + 2 <= min_dim;
+        if (!use_stream && p.kernel == HMI_KERNEL_STREAM) {
+            delete s;
+            return fail(HMI_ERR_UNSUPPORTED, "grid too small for the streaming kernel");
+        }
+        if (!use_stream) tb = 1;
+    }
+    s->use_stream = use_stream;
+    s->tb = tb;
+
+    const int mb_gen = hmi::generic_max_blocks(s->phys_rows, p.cols);
+    const int mb_str = hmi::stream_max_blocks(p.method, s->phys_rows, p.cols);
+    s->max_blocks = mb_gen > mb_str ? mb_gen : mb_str;
+
+    const size_t grid_bytes = (size_t)s->phys_rows * s->pitch * s->elem;
+    const size_t mask_bytes = (size_t)s->phys_rows * s->mpitch;
+    int rc = HMI_OK;
+    do {
+        if ((e = cudaMalloc((void **)&s->buf[0], grid_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&s->buf[1], grid_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&s->mask, mask_bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&s->d_partials, (size_t)s->max_blocks * 4 * sizeof(double))) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&s->d_counter, sizeof(unsigned int))) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&s->d_result, 4 * sizeof(double))) != cudaSuccess) break;
+        if ((e = cudaMallocHost((void **)&s->h_result, 4 * sizeof(double))) != cudaSuccess) break;
+        if ((e = cudaMemset(s->buf[0], 0, grid_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemset(s->buf[1], 0, grid_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemset(s->mask, 1, mask_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemset(s->d_counter, 0, sizeof(unsigned int))) != cudaSuccess) break;
+        if ((e = cudaMemset(s->d_result, 0, 4 * sizeof(double))) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) {
+        rc = fail(HMI_ERR_CUDA, "device allocation failed (%zu bytes per grid): %s", grid_bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        destroy(s);
+        return rc;
+    }
+    *out = s;
+    return HMI_OK;
+}
+
+void hmi_destroy(hmi_solver *s) { destroy(s); }
+
+int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
+{
+    if (!s || !key) return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (!strcmp(key, "chunk_rows")) {
+        if (value < 0) return fail(HMI_ERR_BAD_ARG, "chunk_rows must be >= 0");
+        s->chunk_rows = value == 0 ? 0 : (value < 8 ? 8 : (int)value);
+        return HMI_OK;
+    }
+    if (!strcmp(key, "temporal_block")) {
+        if (!s->use_stream) return fail(HMI_ERR_UNSUPPORTED, "temporal_block applies to the streaming kernel");
+        const int maxk = hmi::stream_max_k(s->p.method, s->p.dtype);
+        const int min_dim = s->p.cols < s->p.rows ? s->p.cols : s->p.rows;
+        if (value < 1 || value > maxk || 2 * hmi::stream_halo(s->p.method, (int)value) + 2 > min_dim)
+            return fail(HMI_ERR_BAD_ARG, "temporal_block out of range");
+        s->tb = (int)value;
+        return HMI_OK;
+    }
+    return fail(HMI_ERR_BAD_ARG, "unknown option '%s'", key);
+}
+
+int hmi_set_problem_host(hmi_solver *s, const void *image, size_t image_pitch_bytes,
+                         const uint8_t *mask, size_t mask_pitch_bytes)
+{
+    if (!s || !image || !mask) return fail(HMI_ERR_BAD_ARG, "null argument");
+    const size_t wbytes = (size_t)s->p.cols * s->elem;
+    if (image_pitch_bytes < wbytes || mask_pitch_bytes < (size_t)s->p.cols)
+        return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    s->cur = 0;
+    CUDA_TRY(cudaMemcpy2D(s->buf[0], (size_t)s->pitch * s->elem, image, image_pitch_bytes, wbytes,
+                          s->phys_rows, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy2D(s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
+                          s->phys_rows, cudaMemcpyHostToDevice));
+    s->has_problem = true;
+    return HMI_OK;
+}
+
+int hmi_set_problem_device(hmi_solver *s, const void *image_dev, size_t image_pitch_bytes,
+                           const uint8_t *mask_dev, size_t mask_pitch_bytes, void *stream)
+{
+    if (!s || !image_dev || !mask_dev) return fail(HMI_ERR_BAD_ARG, "null argument");
+    const size_t wbytes = (size_t)s->p.cols * s->elem;
+    if (image_pitch_bytes < wbytes || mask_pitch_bytes < (size_t)s->p.cols)
+        return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    s->cur = 0;
+    CUDA_TRY(cudaMemcpy2DAsync(s->buf[0], (size_t)s->pitch * s->elem, image_dev, image_pitch_bytes,
+                               wbytes, s->phys_rows, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(s->mask, (size_t)s->mpitch, mask_dev, mask_pitch_bytes,
+                               (size_t)s->p.cols, s->phys_rows, cudaMemcpyDeviceToDevice, st));
+    s->has_problem = true;
+    return HMI_OK;
+}
+
+int hmi_sweeps(hmi_solver *s, int64_t n, void *stream)
+{
+    if (!s) return fail(HMI_ERR_BAD_ARG, "null solver");
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    return do_sweeps(s, n, false, (cudaStream_t)stream);
+}
+
+int hmi_sweeps_norm(hmi_solver *s, int64_t n, void *stream, hmi_norm *out)
+{
+    if (!s || !out) return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (n < 1) return fail(HMI_ERR_BAD_ARG, "hmi_sweeps_norm needs n >= 1");
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    const int rc = do_sweeps(s, n, true, (cudaStream_t)stream);
+    if (rc != HMI_OK) return rc;
+    return fetch_norm(s, (cudaStream_t)stream, out);
+}
+
+int hmi_run(hmi_solver *s, void *stream, hmi_status *status)
+{
+    if (!s || !status) return fail(HMI_ERR_BAD_ARG, "null argument");
+    const hmi_params &p = s->p;
+    if (p.ghost_top || p.ghost_bottom)
+        return fail(HMI_ERR_STATE, "hmi_run drives a whole grid; slabs are driven by the host layer");
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "hmi_set_problem_* has not been called");
+    CUDA_TRY(cudaSetDevice(p.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long T = p.term_check_iters, maxit = p.max_iters;
+    long long i = 0;
+    status->updates_done = 0;
+    status->last_diff = 100000.0;  // fd_pde_inpainter.py:309
+    status->converged = 0;
+    status->checks = 0;
+    while (i < maxit) {
+        const long long c = (i + T - 1) / T * T;  // next iteration index with c % T == 0
+        if (c >= maxit) {                         // no check left before max_iters
+            const int rc = do_sweeps(s, maxit - i, false, st);
+            if (rc != HMI_OK) return rc;
+            i = maxit;
+            break;
+        }
+        hmi_norm nm;
+        int rc = do_sweeps(s, c - i + 1, true, st);
+        if (rc != HMI_OK) return rc;
+        rc = fetch_norm(s, st, &nm);
+        if (rc != HMI_OK) return rc;
+        i = c + 1;
+        status->checks += 1;
+        status->last_diff = norm_to_diff(p, nm);
+        if (status->last_diff < p.term_thres) {   // NaN compares false: never terminates on NaN
+            status->converged = 1;
+            break;
+        }
+    }
+    status->updates_done = i;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return HMI_OK;
+}
+
+int hmi_get_result_host(hmi_solver *s, void *out, size_t out_pitch_bytes)
+{
+    if (!s || !out) return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "no problem loaded");
+    const size_t wbytes = (size_t)s->p.cols * s->elem;
+    if (out_pitch_bytes < wbytes) return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const char *src = s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
+    CUDA_TRY(cudaMemcpy2D(out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows,
+                          cudaMemcpyDeviceToHost));
+    return HMI_OK;
+}
+
+int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, void *stream)
+{
+    if (!s || !out_dev) return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "no problem loaded");
+    const size_t wbytes = (size_t)s->p.cols * s->elem;
+    if (out_pitch_bytes < wbytes) return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    const char *src = s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
+    CUDA_TRY(cudaMemcpy2DAsync(out_dev, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes,
+                               s->p.rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HMI_OK;
+}
+
+int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
+                     hmi_status *status)
+{
+    if (!params || !image || !mask || !out || !status) return fail(HMI_ERR_BAD_ARG, "null argument");
+    hmi_solver *s = nullptr;
+    int rc = hmi_create(params, &s);
+    if (rc != HMI_OK) return rc;
+    const size_t elem = params->dtype == HMI_F64 ? 8 : 4;
+    rc = hmi_set_problem_host(s, image, (size_t)params->cols * elem, mask, (size_t)params->cols);
+    if (rc == HMI_OK) rc = hmi_run(s, nullptr, status);
+    if (rc == HMI_OK) rc = hmi_get_result_host(s, out, (size_t)params->cols * elem);
+    hmi_destroy(s);
+    return rc;
+}
+
+int hmi_current_grid(hmi_solver *s, void **grid_dev, size_t *pitch_bytes)
+{
+    if (!s || !grid_dev || !pitch_bytes) return fail(HMI_ERR_BAD_ARG, "null argument");
+    *grid_dev = s->buf[s->cur];
+    *pitch_bytes = (size_t)s->pitch * s->elem;
+    return HMI_OK;
+}
+
+int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes)
+{
+    if (!s || !mask_dev || !pitch_bytes) return fail(HMI_ERR_BAD_ARG, "null argument");
+    *mask_dev = s->mask;
+    *pitch_bytes = (size_t)s->mpitch;
+    return HMI_OK;
+}
+
+int hmi_temporal_block(const hmi_solver *s) { return s ? s->tb : 0; }
+int64_t hmi_launch_count(const hmi_solver *s) { return s ? s->launches : 0; }
+const char *hmi_kernel_name(const hmi_solver *s) { return !s ? "" : (s->use_stream ? "stream" : "generic"); }
+
+}  // extern "C"

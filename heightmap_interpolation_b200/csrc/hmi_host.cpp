@@ -1,0 +1,96 @@
+// Host-side initialiser helpers of the C ABI (include/hmi_b200.h): the 'zeros' / 'mean' fillers of
+// the reference's Initializer (heightmap_interpolation/inpainting/initializer.py:15-18), done in
+// place on the caller's host array with a few threads and branch-free inner loops.
+#include <cmath>
+#include <cstdint>
+#include <thread>
+#include <vector>
+
+#include "../../include/hmi_b200.h"
+
+namespace {
+
+int num_threads(int64_t n)
+{
+    if (n < (1 << 16)) return 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw == 0 ? 4 : (hw > 16 ? 16 : (int)hw);
+}
+
+template <typename T>
+void fill_range(T *__restrict__ img, const uint8_t *__restrict__ mask, int64_t a, int64_t b, T v)
+{
+    for (int64_t i = a; i < b; ++i) img[i] = mask[i] ? img[i] : v;
+}
+
+template <typename T>
+void fill_unknown(T *img, const uint8_t *mask, int64_t n, T v)
+{
+    const int nt = num_threads(n);
+    const int64_t per = (n + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const int64_t a = t * per, b = (a + per < n) ? a + per : n;
+        if (a < b) th.emplace_back(fill_range<T>, img, mask, a, b, v);
+    }
+    fill_range<T>(img, mask, 0, per < n ? per : n, v);
+    for (auto &x : th) x.join();
+}
+
+template <typename T>
+void sum_range(const T *__restrict__ img, const uint8_t *__restrict__ mask, int64_t a, int64_t b,
+               double *sum, int64_t *cnt)
+{
+    double s = 0.0;
+    int64_t c = 0;
+    for (int64_t i = a; i < b; ++i) {
+        s += mask[i] ? (double)img[i] : 0.0;
+        c += mask[i] ? 1 : 0;
+    }
+    *sum = s;
+    *cnt = c;
+}
+
+template <typename T>
+double known_mean(const T *img, const uint8_t *mask, int64_t n)
+{
+    const int nt = num_threads(n);
+    const int64_t per = (n + nt - 1) / nt;
+    std::vector<double> sums(nt, 0.0);
+    std::vector<int64_t> cnts(nt, 0);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const int64_t a = t * per, b = (a + per < n) ? a + per : n;
+        if (a < b) th.emplace_back(sum_range<T>, img, mask, a, b, &sums[t], &cnts[t]);
+    }
+    sum_range<T>(img, mask, 0, per < n ? per : n, &sums[0], &cnts[0]);
+    for (auto &x : th) x.join();
+    double s = 0.0;
+    int64_t c = 0;
+    for (int t = 0; t < nt; ++t) { s += sums[t]; c += cnts[t]; }
+    return c ? s / (double)c : std::nan("");
+}
+
+}  // namespace
+
+extern "C" {
+
+int hmi_host_fill_unknown(void *image, const uint8_t *mask, int64_t n, int32_t dtype, double value)
+{
+    if (!image || !mask || n < 0) return HMI_ERR_BAD_ARG;
+    if (dtype == HMI_F64) fill_unknown<double>((double *)image, mask, n, value);
+    else if (dtype == HMI_F32) fill_unknown<float>((float *)image, mask, n, (float)value);
+    else return HMI_ERR_BAD_ARG;
+    return HMI_OK;
+}
+
+int hmi_host_known_mean(const void *image, const uint8_t *mask, int64_t n, int32_t dtype, double *mean)
+{
+    if (!image || !mask || !mean || n < 0) return HMI_ERR_BAD_ARG;
+    if (dtype == HMI_F64) *mean = known_mean<double>((const double *)image, mask, n);
+    else if (dtype == HMI_F32) *mean = known_mean<float>((const float *)image, mask, n);
+    else return HMI_ERR_BAD_ARG;
+    return HMI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// Interface of the streaming temporal-blocked kernel (hmi_stream.cu).
+#pragma once
+
+#include "hmi_common.cuh"
+
+namespace hmi {
+
+constexpr int STREAM_MAX_K_HARMONIC = 8;
+constexpr int STREAM_MAX_K_CCST = 4;
+
+template <typename T>
+struct StreamArgs {
+    const T *src;
+    T *dst;
+    const uint8_t *mask;
+    long long pitch, mpitch;
+    int rows, cols;             // interior rows of the slab, columns
+    int row_lo, row_hi;         // rows written by this launch [row_lo, row_hi)
+    int read_lo, read_hi;       // rows that exist in memory [read_lo, read_hi) (ghosts included)
+    int top_border, bottom_border;
+    int chunk_rows;             // rows per warp chunk; <= 0 = auto
+    int nwin, nchunks;          // filled by the launcher
+    T dt, tension, one_minus_tension;
+    int do_norm;
+    double *partials;
+    unsigned int *counter;
+    double *result;
+};
+
+// k sweeps fused in one launch.  method in {HMI_HARMONIC, HMI_CCST}, 1 <= k <= stream_max_k().
+template <typename T>
+cudaError_t launch_stream(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out);
+
+int stream_max_k(int method, int dtype);
+int stream_halo(int method, int k);                 // ghost rows/columns k fused sweeps consume
+int stream_auto_chunk_rows(int nrows, int nwin, int halo);
+int stream_max_blocks(int method, int rows_total, int cols);
+
+}  // namespace hmi

@@ -1,0 +1,200 @@
+"""Row-slab domain decomposition across the GPUs of one box (one process per GPU).
+
+The reference is a single process holding the whole grid; this module is the only
+parallelism the path admits: every sweep is a local stencil, so the grid is cut into contiguous row
+slabs, each slab carries `ghost` rows of its neighbours above and below, and
+
+  * every `exchange_every` sweeps the ghost rows are refreshed with one grouped send/recv per
+    neighbour (NCCL over NVLink; gloo in the CPU tests).  Between exchanges the solver advances a
+    shrinking trapezoid of ghost rows itself (see hmi_sweeps in include/hmi_b200.h), so
+    ghost = radius * exchange_every rows buy `exchange_every` sweeps per exchange;
+  * on a check iteration the per-slab convergence sums are all-reduced (sum, sum, max, max) — the
+    only global quantity of the loop (fd_pde_inpainter.py:368-379);
+  * the reflect-101 / zero border rule applies only at the global top and bottom, never at seams.
+
+`torch.distributed` is plumbing only: it moves ghost rows and four doubles.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi as C
+from .solver import Norm, Solver
+
+
+def slab_bounds(rows, world):
+    """Contiguous, near-equal row ranges [r0, r1) for each rank."""
+    base, rem = divmod(int(rows), int(world))
+    out, r0 = [], 0
+    for k in range(world):
+        r1 = r0 + base + (1 if k < rem else 0)
+        out.append((r0, r1))
+        r0 = r1
+    return out
+
+
+class _DevArray:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr, strides=None):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2,
+                                         "strides": strides}
+
+
+class CudaSlabEngine:
+    """The CUDA solver of one slab plus zero-copy torch views of its ghost/edge rows."""
+
+    def __init__(self, params):
+        self.solver = Solver(params)
+        self.params = params
+        self.device = torch.device("cuda", params.device)
+        self.typestr = "<f8" if params.dtype == C.HMI_F64 else "<f4"
+        self.elem = 8 if params.dtype == C.HMI_F64 else 4
+
+    def load(self, image, mask):
+        self.solver.set_problem_host(image, mask)
+
+    def _grid(self):
+        ptr, pitch = self.solver.current_grid()
+        rows = self.solver.phys_rows
+        arr = _DevArray(ptr, (rows, pitch // self.elem), self.typestr)
+        return torch.as_tensor(arr, device=self.device)
+
+    def rows_view(self, lo, hi):
+        """Physical rows [lo, hi) of the current iterate (row 0 = first ghost row), pitched."""
+        return self._grid()[lo:hi]
+
+    def sweeps(self, n):
+        self.solver.sweeps(n)
+
+    def sweeps_norm(self, n):
+        return self.solver.sweeps_norm(n)
+
+    def result(self):
+        return self.solver.get_result_host()
+
+    def close(self):
+        self.solver.close()
+
+
+class SlabSolver:
+    """One rank's share of a row-slab decomposed solve.  Provides the sweeps()/sweeps_norm()
+    surface FDPDEInpainter._loop drives, so the reference's loop semantics are shared with the
+    single-GPU path."""
+
+    def __init__(self, engine, rank, world, radius, ghost_top, ghost_bottom, exchange_every,
+                 rows, group=None):
+        self.engine, self.rank, self.world, self.group = engine, rank, world, group
+        self.radius = radius
+        self.gt, self.gb = ghost_top, ghost_bottom
+        self.rows = rows
+        self.exchange_every = int(exchange_every)
+        if world > 1 and self.exchange_every * radius > max(ghost_top, ghost_bottom):
+            raise ValueError("exchange_every*radius exceeds the ghost depth")
+        self.exchanges = 0
+
+    # -- halo exchange: my first/last `g` interior rows -> the neighbour's ghost rows
+    def exchange(self):
+        if self.world == 1:
+            return
+        ops, keep = [], []
+        e, gt, gb, R = self.engine, self.gt, self.gb, self.rows
+        if self.rank > 0:                      # neighbour above
+            send = e.rows_view(gt, gt + gt)    # my top gt interior rows (its bottom ghost depth == gt)
+            recv = e.rows_view(0, gt)
+            ops += [dist.P2POp(dist.isend, send, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, recv, self.rank - 1, self.group)]
+            keep += [send, recv]
+        if self.rank < self.world - 1:         # neighbour below
+            send = e.rows_view(gt + R - gb, gt + R)
+            recv = e.rows_view(gt + R, gt + R + gb)
+            ops += [dist.P2POp(dist.isend, send, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, recv, self.rank + 1, self.group)]
+            keep += [send, recv]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.exchanges += 1
+
+    def _blocks(self, n):
+        E = self.exchange_every if self.world > 1 else max(n, 1)
+        while n > 0:
+            k = min(n, E)
+            yield k
+            n -= k
+
+    def sweeps(self, n):
+        for k in self._blocks(int(n)):
+            self.exchange()
+            self.engine.sweeps(k)
+
+    def sweeps_norm(self, n):
+        n = int(n)
+        blocks = list(self._blocks(n))
+        for k in blocks[:-1]:
+            self.exchange()
+            self.engine.sweeps(k)
+        self.exchange()
+        nm = self.engine.sweeps_norm(blocks[-1])
+        return self.allreduce_norm(nm)
+
+    def allreduce_norm(self, nm):
+        if self.world == 1:
+            return nm
+        dev = getattr(self.engine, "device", torch.device("cpu"))
+        sums = torch.tensor([nm.sum_d2, nm.sum_f2], dtype=torch.float64, device=dev)
+        maxs = torch.tensor([nm.max_abs, nm.has_nan], dtype=torch.float64, device=dev)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=self.group)
+        sums, maxs = sums.cpu(), maxs.cpu()
+        return Norm(float(sums[0]), float(sums[1]), float(maxs[0]), float(maxs[1]))
+
+
+def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=None,
+                 engine_factory=None, group=None):
+    """Distributed `inpaint_grid`: every rank passes the same global `image`/`mask` (already
+    initialised, host arrays) or — to save host memory — any arrays whose rows [r0-ghost, r1+ghost)
+    are valid; returns this rank's interior rows and its (r0, r1).
+
+    The loop semantics (check cadence, stop rule, progress table on rank 0) are those of
+    FDPDEInpainter._loop.  `engine_factory(params)` exists for the CPU tests (gloo + a CPU engine);
+    the product path always builds CudaSlabEngine.
+    """
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
+    rows, cols = image.shape
+    radius = 2 if inpainter.METHOD == C.HMI_CCST else 1
+    bounds = slab_bounds(rows, world)
+    r0, r1 = bounds[rank]
+    min_rows = min(b - a for a, b in bounds)
+    if exchange_every is None:
+        exchange_every = 16 if radius == 1 else 8
+    exchange_every = max(1, min(int(exchange_every), (min_rows - 1) // radius if world > 1 else 10 ** 9))
+    ghost = radius * exchange_every if world > 1 else 0
+    gt = ghost if rank > 0 else 0
+    gb = ghost if rank < world - 1 else 0
+
+    inpainter.set_term_criteria(image)   # every rank sees the same global z-range
+    device = inpainter._device() if engine_factory is None else 0
+    params = inpainter._make_params(r1 - r0, cols, image.dtype, ghost_top=gt, ghost_bottom=gb,
+                                    device=device)
+    engine = (engine_factory or CudaSlabEngine)(params)
+    try:
+        engine.load(np.ascontiguousarray(image[r0 - gt:r1 + gb]),
+                    np.ascontiguousarray(mask[r0 - gt:r1 + gb]))
+        slab = SlabSolver(engine, rank, world, radius, gt, gb, exchange_every, r1 - r0, group)
+        quiet = inpainter.print_progress and rank != 0
+        if quiet:
+            inpainter.print_progress = False
+        try:
+            done, diff, conv = inpainter._loop(slab, params.criteria)
+        finally:
+            if quiet:
+                inpainter.print_progress = True
+        inpainter._record(done, diff, conv, getattr(engine, "kernel_name", None), None)
+        inpainter.exchanges_ = slab.exchanges
+        if not conv and rank == 0:
+            print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
+        return engine.result(), (r0, r1)
+    finally:
+        engine.close()

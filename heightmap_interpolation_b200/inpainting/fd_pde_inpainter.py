@@ -1,0 +1,253 @@
+"""B200 drop-in for the reference's FD-PDE inpainter base class.
+
+Mirrors ``heightmap_interpolation/inpainting/fd_pde_inpainter.py`` of the reference (v1.0.7):
+same constructor keywords, defaults and ``ValueError`` messages (:71-100), ``get_config`` (:124-139),
+``set_term_criteria`` (:141-158), ``inpaint`` (:160-185) and the loop semantics of ``inpaint_grid``
+(:281-366).  The loop body itself — step function, mask-constrained update, over-relaxation and the
+convergence norm — runs in hand-written CUDA kernels behind the C ABI of ``include/hmi_b200.h``.
+
+Extra keywords (ignored by the reference, which silently drops unknown keys):
+``device`` (CUDA ordinal), ``kernel`` ("auto" | "generic" | "stream"), ``temporal_block`` (sweeps fused
+per launch, 0 = auto).  After a solve the object exposes ``iterations_``, ``last_diff_`` and
+``converged_`` (the reference only prints them).
+"""
+import math
+from abc import ABC
+from timeit import default_timer as timer
+
+import numpy as np
+
+from .. import _capi as C
+from ..solver import Norm, Solver, inpaint_host, make_params
+from .convolver import Convolver
+from .initializer import Initializer
+
+
+class FDPDEInpainter(ABC):
+    """Abstract base of the explicit finite-difference PDE inpainters (reference class of the same name)."""
+
+    METHOD = None  # hmi_method code, set by subclasses
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        # --- same keywords and defaults as the reference (fd_pde_inpainter.py:71-84)
+        self.dt = kwargs.pop("update_step_size", 0.01)
+        self.term_check_iters = kwargs.pop("term_check_iters", 1000)
+        self.term_thres = kwargs.pop("term_thres", 1e-8)
+        self.max_iters = int(kwargs.pop("max_iters", 1e8))
+        self.relaxation = kwargs.pop("relaxation", 0)
+        self.print_progress = kwargs.pop("print_progress", False)
+        self.print_progress_iters = kwargs.pop("print_progress_iters", 1000)
+        self.mgs_levels = kwargs.pop("mgs_levels", 1)
+        self.mgs_min_res = kwargs.pop("mgs_min_res", 100)
+        self.init_with = kwargs.pop("init_with", "zeros")
+        self.convolver_type = kwargs.pop("convolver", "masked")
+        self.convolver = Convolver(self.convolver_type)
+        self.debug_dir = kwargs.pop("debug_dir", "")
+        self.term_criteria = kwargs.pop("term_criteria", "relative")
+        self.ts = 0
+        # --- B200 back-end keywords
+        self.device = kwargs.pop("device", None)
+        self.kernel = kwargs.pop("kernel", "auto")
+        self.temporal_block = int(kwargs.pop("temporal_block", 0))
+
+        # --- same validation, same messages (fd_pde_inpainter.py:87-100)
+        if self.dt <= 0:
+            raise ValueError("update_step_size must be larger than zero")
+        if self.term_thres <= 0:
+            raise ValueError("term_thres must be larger than zero")
+        if self.max_iters <= 0:
+            raise ValueError("max_iters must be larger than zero")
+        if self.relaxation != 0.0 and (self.relaxation < 1.0 or self.relaxation > 2.0):
+            raise ValueError("relaxation must be a number between 1 and 2 (0 to deactivate)")
+        if not isinstance(self.max_iters, int):
+            raise ValueError("max_iters must be an integer")
+        if not isinstance(self.mgs_levels, int):
+            raise ValueError("mgs_levels must be an integer")
+        if not isinstance(self.mgs_min_res, int):
+            raise ValueError("mgs_min_res must be an integer")
+        if self.kernel not in C.KERNELS:
+            raise ValueError("kernel must be one of: " + ", ".join(C.KERNELS))
+        if self.debug_dir:
+            raise NotImplementedError("debug_dir (matplotlib PNG dumps) is not part of the B200 back-end")
+
+        self.map_term_criteria_str_to_int = {"relative": 0, "absolute": 1, "absolute_percent": 2}
+        self.print_progress_table_row_str = "|{:>11d}|{:>17.10f}|"
+        self.print_progress_last_table_row_str = "| CONVERGED |{:>17.10f}|"
+        self.initializer = Initializer(self.init_with)
+
+        # results of the last solve
+        self.iterations_ = None
+        self.last_diff_ = None
+        self.converged_ = None
+        self.kernel_name_ = None
+        self.launches_ = None
+
+    # ------------------------------------------------------------------ configuration
+    def get_config(self):
+        return {"update_step_size": self.dt,
+                "term_criteria": self.term_criteria,
+                "term_check_iters": self.term_check_iters,
+                "term_thres": self.term_thres,
+                "max_iters": self.max_iters,
+                "relaxation": self.relaxation,
+                "print_progress": self.print_progress,
+                "print_progress_iters": self.print_progress_iters,
+                "mgs_levels": self.mgs_levels,
+                "mgs_min_res": self.mgs_min_res,
+                "init_with": self.init_with,
+                "convolver": self.convolver_type}
+
+    def set_term_criteria(self, f):
+        """fd_pde_inpainter.py:141-158, including the in-place scaling of term_thres."""
+        self.term_criteria_int = self.map_term_criteria_str_to_int.get(self.term_criteria, -1)
+        if self.term_criteria_int == 0:
+            self.print_msg("* Termination criteria --> relative change = {:f}".format(self.term_thres))
+        elif self.term_criteria_int == 1:
+            self.print_msg("* Termination criteria --> absolute change = {:f}".format(self.term_thres))
+        elif self.term_criteria_int == 2:
+            max_val = np.max(f)
+            min_val = np.min(f)
+            z_range = abs(max_val - min_val)
+            self.print_msg("* Termination criteria --> absolute percent change:")
+            self.print_msg(f"    - Abs. Z range: {z_range:f}")
+            self.print_msg(f"    - Percent = {self.term_thres:f}")
+            self.term_thres = z_range * self.term_thres
+            self.print_msg(f"    - Terminate if absolute change < {self.term_thres:f}")
+        else:
+            raise ValueError("Unknown termination criteria!")
+
+    # subclass hooks ----------------------------------------------------------------
+    def _method_params(self):
+        """Extra numeric options of the subclass (tension / epsilon)."""
+        return {}
+
+    def step_fun(self, f, mask):
+        """The reference evaluates one step function on the host (abstract hook, :406-408).  Here the
+        step functions only exist fused inside the sweep kernels; use ``sweeps(...)`` instead."""
+        raise NotImplementedError("step_fun is fused into the CUDA sweep kernels of the B200 back-end")
+
+    # ------------------------------------------------------------------ public API
+    def inpaint(self, image, mask, out=None):
+        """Inpaint `image` where `mask` is False (True == known).  Same contract as the reference
+        (:160-185): the caller's `image` is initialised IN PLACE, a new array is returned.
+        `out` is an extension: a preallocated (e.g. pinned) array to receive the result."""
+        self.print_msg("*** INPAINTING ***")
+        if self.mgs_levels > 1:
+            self.print_msg("* Using a multi-grid solver")
+            from .multigrid import inpaint_multigrid
+            return inpaint_multigrid(self, image, mask)
+        self.print_msg("* Initializing the inpainting problem using the '{:s}' filler".format(self.init_with))
+        image = self.initializer.initialize(image, mask)
+        self.print_msg("* Optimization:")
+        return self.inpaint_grid(image, mask, out)
+
+    def _device(self):
+        return 0 if self.device is None else int(self.device)
+
+    def _make_params(self, rows, cols, dtype, **over):
+        kw = dict(rows=rows, cols=cols, dtype=dtype, method=self.METHOD,
+                  orientation=self.convolver.orientation, border=self.convolver.border,
+                  criteria=C.HMI_RELATIVE if self.term_criteria_int == 0 else C.HMI_ABSOLUTE,
+                  dt=self.dt, relaxation=self.relaxation, term_thres=self.term_thres,
+                  term_check_iters=self.term_check_iters, max_iters=self.max_iters,
+                  device=self._device(), kernel=C.KERNELS[self.kernel],
+                  temporal_block=self.temporal_block)
+        kw.update(self._method_params())
+        kw.update(over)
+        return make_params(**kw)
+
+    def inpaint_grid(self, image, mask, out=None):
+        """Single-scale solve (fd_pde_inpainter.py:281-366) on one B200."""
+        image, mask = _check_inputs(image, mask)
+        self.set_term_criteria(image)
+        if self.term_check_iters <= 0:
+            raise ZeroDivisionError("integer modulo by zero")  # what `i % 0` raises in the reference (:322)
+        params = self._make_params(image.shape[0], image.shape[1], image.dtype)
+        if not self.print_progress:
+            out, st = inpaint_host(params, image, mask, out)
+            self._record(st.updates_done, st.last_diff, bool(st.converged), None, None)
+        else:
+            with Solver(params) as s:
+                s.set_problem_host(image, mask)
+                done, diff, conv = self._loop(s, params.criteria)
+                out = s.get_result_host(out)
+                self._record(done, diff, conv, s.kernel_name, s.launch_count)
+        if not self.converged_:
+            print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
+        return out
+
+    def _record(self, done, diff, conv, kernel_name, launches):
+        self.iterations_, self.last_diff_, self.converged_ = int(done), float(diff), bool(conv)
+        self.kernel_name_, self.launches_ = kernel_name, launches
+
+    def _loop(self, engine, criteria):
+        """The reference loop, event driven: sweeps are issued in batches up to the next iteration
+        index at which the reference does something observable (a check at i % T == 0, a progress
+        row at i % P == 0, or the last iteration).  `engine` provides sweeps(n) / sweeps_norm(n)."""
+        T, P, maxit = int(self.term_check_iters), int(self.print_progress_iters), int(self.max_iters)
+        show = self.print_progress and P > 0
+        diff = 100000
+        terminate = False
+        i = 0
+        while i < maxit:
+            nxt = (i + T - 1) // T * T
+            if show:
+                nxt = min(nxt, (i + P - 1) // P * P)
+            e = min(nxt, maxit - 1)
+            n = e - i + 1
+            is_check = (e % T == 0)
+            if is_check:
+                nm = engine.sweeps_norm(n)
+                diff = nm.diff(criteria)
+                terminate = diff < self.term_thres
+            else:
+                engine.sweeps(n)
+            if show and e % P == 0:
+                if e == 0:
+                    print("+-----------+-----------------+")
+                    print("| Iteration | Function change |")
+                    print("+-----------+-----------------+")
+                print(self.print_progress_table_row_str.format(e, diff))
+            i = e + 1
+            if is_check and terminate:
+                if self.print_progress:
+                    print("+-----------+-----------------+")
+                    print(self.print_progress_last_table_row_str.format(diff))
+                    print("+-----------+-----------------+")
+                return i, diff, True
+        return i, diff, False
+
+    # ------------------------------------------------------------------ printing utilities (:386-404)
+    def print_start(self, msg):
+        if self.print_progress:
+            print(msg, end='')
+            self.ts = timer()
+
+    def print_end(self):
+        if self.print_progress:
+            te = timer()
+            print("done ({:.2f} s)".format(te - self.ts))
+
+    def print_msg(self, msg):
+        if self.print_progress:
+            print(msg)
+
+    def get_decimal_places(self, number):
+        if math.floor(number) == number:
+            return 0
+        return len("{:f}".format(number).split(".")[1])
+
+
+def _check_inputs(image, mask):
+    image = np.asarray(image)
+    mask = np.asarray(mask)
+    if image.ndim != 2:
+        raise ValueError("image must be a 2-D array")
+    if mask.shape != image.shape:
+        raise ValueError("mask must have the same shape as the image")
+    if image.dtype not in (np.float32, np.float64):
+        raise TypeError("image dtype must be float32 or float64, got %s" % image.dtype)
+    if mask.dtype != np.bool_:
+        mask = mask != 0
+    return np.ascontiguousarray(image), np.ascontiguousarray(mask)

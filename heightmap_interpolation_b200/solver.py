@@ -1,0 +1,173 @@
+"""Thin RAII wrapper over the C-ABI solver handle (include/hmi_b200.h)."""
+import ctypes
+
+import numpy as np
+
+from . import _capi as C
+
+_DTYPES = {np.dtype(np.float32): C.HMI_F32, np.dtype(np.float64): C.HMI_F64}
+
+
+def dtype_code(dtype):
+    try:
+        return _DTYPES[np.dtype(dtype)]
+    except KeyError:
+        raise TypeError("grid dtype must be float32 or float64, got %s" % (dtype,))
+
+
+def make_params(rows, cols, dtype, method, orientation=1, border=C.HMI_BORDER_REFLECT101,
+                criteria=C.HMI_RELATIVE, dt=0.01, tension=0.0, epsilon=1e-2, relaxation=0.0,
+                term_thres=1e-8, term_check_iters=1000, max_iters=int(1e8), device=0,
+                kernel=C.HMI_KERNEL_AUTO, temporal_block=0, ghost_top=0, ghost_bottom=0):
+    p = C.HmiParams()
+    p.struct_size = ctypes.sizeof(C.HmiParams)
+    p.device = int(device)
+    p.rows, p.cols = int(rows), int(cols)
+    p.dtype = dtype_code(dtype)
+    p.method = int(method)
+    p.orientation = int(orientation)
+    p.border = int(border)
+    p.criteria = int(criteria)
+    p.kernel = int(kernel)
+    p.temporal_block = int(temporal_block)
+    p.ghost_top, p.ghost_bottom = int(ghost_top), int(ghost_bottom)
+    p.dt, p.tension, p.epsilon = float(dt), float(tension), float(epsilon)
+    p.relaxation = float(relaxation)
+    p.term_thres = float(term_thres)
+    p.term_check_iters = int(term_check_iters)
+    p.max_iters = int(max_iters)
+    return p
+
+
+class Norm:
+    """Convergence sums of one slab (hmi_norm)."""
+    __slots__ = ("sum_d2", "sum_f2", "max_abs", "has_nan")
+
+    def __init__(self, sum_d2=0.0, sum_f2=0.0, max_abs=0.0, has_nan=0.0):
+        self.sum_d2, self.sum_f2, self.max_abs, self.has_nan = sum_d2, sum_f2, max_abs, has_nan
+
+    def diff(self, criteria):
+        """term_check(): fd_pde_inpainter.py:368-379."""
+        if criteria == C.HMI_RELATIVE:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                return float(np.sqrt(np.float64(self.sum_d2)) / np.sqrt(np.float64(self.sum_f2)))
+        return float("nan") if self.has_nan else float(self.max_abs)
+
+
+class Solver:
+    """One grid (or one row slab) resident on one B200."""
+
+    def __init__(self, params):
+        self._lib = C.lib()
+        self.params = params
+        h = ctypes.c_void_p()
+        C.check(self._lib.hmi_create(ctypes.byref(params), ctypes.byref(h)))
+        self._h = h
+        self.np_dtype = np.float64 if params.dtype == C.HMI_F64 else np.float32
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hmi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- problem
+    @property
+    def phys_rows(self):
+        p = self.params
+        return p.ghost_top + p.rows + p.ghost_bottom
+
+    def set_problem_host(self, image, mask):
+        image = np.ascontiguousarray(image, dtype=self.np_dtype)
+        m8 = np.ascontiguousarray(mask).view(np.uint8) if mask.dtype == np.bool_ else \
+            np.ascontiguousarray(mask, dtype=np.uint8)
+        want = (self.phys_rows, self.params.cols)
+        if image.shape != want or m8.shape != want:
+            raise ValueError("image/mask shape %s/%s, solver expects %s" % (image.shape, m8.shape, want))
+        C.check(self._lib.hmi_set_problem_host(self._h, image.ctypes.data, image.strides[0],
+                                               m8.ctypes.data, m8.strides[0]))
+
+    def set_problem_device(self, image_ptr, image_pitch, mask_ptr, mask_pitch, stream=0):
+        C.check(self._lib.hmi_set_problem_device(self._h, image_ptr, image_pitch, mask_ptr,
+                                                 mask_pitch, stream))
+
+    # -- compute
+    def sweeps(self, n, stream=0):
+        C.check(self._lib.hmi_sweeps(self._h, int(n), stream))
+
+    def sweeps_norm(self, n, stream=0):
+        nm = C.HmiNorm()
+        C.check(self._lib.hmi_sweeps_norm(self._h, int(n), stream, ctypes.byref(nm)))
+        return Norm(nm.sum_d2, nm.sum_f2, nm.max_abs, nm.has_nan)
+
+    def run(self, stream=0):
+        st = C.HmiStatus()
+        C.check(self._lib.hmi_run(self._h, stream, ctypes.byref(st)))
+        return st
+
+    # -- results
+    def get_result_host(self, out=None):
+        p = self.params
+        if out is None:
+            out = np.empty((p.rows, p.cols), dtype=self.np_dtype)
+        C.check(self._lib.hmi_get_result_host(self._h, out.ctypes.data, out.strides[0]))
+        return out
+
+    def get_result_device(self, out_ptr, out_pitch, stream=0):
+        C.check(self._lib.hmi_get_result_device(self._h, out_ptr, out_pitch, stream))
+
+    def current_grid(self):
+        ptr, pitch = ctypes.c_void_p(), ctypes.c_size_t()
+        C.check(self._lib.hmi_current_grid(self._h, ctypes.byref(ptr), ctypes.byref(pitch)))
+        return ptr.value, pitch.value
+
+    def mask_grid(self):
+        ptr, pitch = ctypes.c_void_p(), ctypes.c_size_t()
+        C.check(self._lib.hmi_mask_grid(self._h, ctypes.byref(ptr), ctypes.byref(pitch)))
+        return ptr.value, pitch.value
+
+    # -- tuning / introspection
+    def set_option(self, key, value):
+        C.check(self._lib.hmi_set_option(self._h, key.encode(), int(value)))
+
+    @property
+    def temporal_block(self):
+        return self._lib.hmi_temporal_block(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.hmi_launch_count(self._h)
+
+    @property
+    def kernel_name(self):
+        return self._lib.hmi_kernel_name(self._h).decode()
+
+
+def inpaint_host(params, image, mask, out=None):
+    """hmi_inpaint_host: one call, host buffers in, host buffer out.  `out` (optional) is a
+    C-contiguous array of the grid's shape and dtype to receive the result, e.g. pinned memory."""
+    lib = C.lib()
+    np_dtype = np.float64 if params.dtype == C.HMI_F64 else np.float32
+    image = np.ascontiguousarray(image, dtype=np_dtype)
+    m8 = np.ascontiguousarray(mask).view(np.uint8) if mask.dtype == np.bool_ else \
+        np.ascontiguousarray(mask, dtype=np.uint8)
+    if out is None:
+        out = np.empty_like(image)
+    elif out.shape != image.shape or out.dtype != image.dtype or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous array of the image's shape and dtype")
+    st = C.HmiStatus()
+    C.check(lib.hmi_inpaint_host(ctypes.byref(params), image.ctypes.data, m8.ctypes.data,
+                                 out.ctypes.data, ctypes.byref(st)))
+    return out, st

@@ -1,0 +1,177 @@
+/*
+ * hmi_b200.h — C ABI of the B200-native FD-PDE inpainting solver.
+ *
+ * The reference (coronis-computing/heightmap_interpolation v1.0.7) is pure Python and has no
+ * native boundary for this path; the boundary it does have is
+ *
+ *     Inpainter(**options).inpaint(image, mask)
+ *         heightmap_interpolation/inpainting/fd_pde_inpainter.py:52-122 (options), :160-185 (inpaint)
+ *     created by  create_inpainter_from_params(params)
+ *         heightmap_interpolation/apps/apps_common.py:172-215
+ *     and called from  interpolate()   heightmap_interpolation/apps/interpolate_netcdf4.py:200-204
+ *
+ * Every entry point below names the reference code it replaces.  All functions return 0 on success
+ * and a negative hmi_error on failure; hmi_last_error() gives the message.  No C++ exceptions and
+ * no torch types cross this boundary: plain pointers, sizes and PODs only.  A solver handle is not
+ * thread-safe.  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef HMI_B200_H
+#define HMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMI_ABI_VERSION 1
+
+typedef struct hmi_solver hmi_solver;
+
+enum hmi_error {
+    HMI_OK = 0,
+    HMI_ERR_BAD_ARG = -1,     /* maps to Python ValueError */
+    HMI_ERR_CUDA = -2,        /* CUDA runtime/driver failure (RuntimeError) */
+    HMI_ERR_NO_DEVICE = -3,   /* no CUDA device / wrong architecture (RuntimeError) */
+    HMI_ERR_STATE = -4,       /* call out of order, e.g. run before set_problem */
+    HMI_ERR_UNSUPPORTED = -5  /* valid in the reference, not built here yet */
+};
+
+enum hmi_dtype { HMI_F32 = 0, HMI_F64 = 1 };
+
+/* Which subclass step function to run:
+ *   HMI_HARMONIC  SobolevInpainter.step_fun   inpainting/sobolev_inpainter.py:15-17
+ *   HMI_CCST      CCSTInpainter.step_fun      inpainting/ccst_inpainter.py:23-34
+ *   HMI_TV        TVInpainter.step_fun        inpainting/tv_inpainter.py:20-33
+ *   HMI_AMLE      AMLEInpainter.step_fun      inpainting/amle_inpainter.py:41-59 (2-D branch) */
+enum hmi_method { HMI_HARMONIC = 0, HMI_CCST = 1, HMI_TV = 2, HMI_AMLE = 3 };
+
+/* The `convolver` option decomposes into an orientation and a border rule
+ * (inpainting/convolver.py:11-69, inpainting/convolve_at_mask.py:39-63):
+ *   "opencv"                    -> +1 (correlation), HMI_BORDER_REFLECT101
+ *   "masked", "masked-parallel" -> -1 (convolution), HMI_BORDER_REFLECT101
+ *   "scipy-signal", "scipy-ndimage" -> -1, HMI_BORDER_ZERO  (convolver.py:17-18 maps both names
+ *                                      to scipy.signal.convolve)
+ *   HMI_BORDER_SYMMETRIC is scipy.ndimage's 'reflect' (only reachable through AMLE convolve_in_1d). */
+enum hmi_border { HMI_BORDER_REFLECT101 = 0, HMI_BORDER_SYMMETRIC = 1, HMI_BORDER_ZERO = 2 };
+
+/* term_check()  inpainting/fd_pde_inpainter.py:368-379.  "absolute_percent" is HMI_ABSOLUTE with
+ * term_thres pre-multiplied by the z-range by the caller (set_term_criteria, :149-155). */
+enum hmi_criteria { HMI_RELATIVE = 0, HMI_ABSOLUTE = 1 };
+
+/* Kernel selection; AUTO is the product default, the others exist for tests and benchmarks. */
+enum hmi_kernel { HMI_KERNEL_AUTO = 0, HMI_KERNEL_GENERIC = 1, HMI_KERNEL_STREAM = 2 };
+
+/* Constructor options (FDPDEInpainter.__init__, inpainting/fd_pde_inpainter.py:71-100, plus the
+ * subclass options tension / epsilon) after the Python layer has validated them. */
+typedef struct hmi_params {
+    int32_t struct_size;      /* sizeof(hmi_params), for ABI checking */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t rows, cols;       /* interior rows of this slab (whole grid on one GPU), columns */
+    int32_t dtype;            /* hmi_dtype: arithmetic follows the input grid's dtype */
+    int32_t method;           /* hmi_method */
+    int32_t orientation;      /* +1 correlation, -1 convolution */
+    int32_t border;           /* hmi_border */
+    int32_t criteria;         /* hmi_criteria */
+    int32_t kernel;           /* hmi_kernel */
+    int32_t temporal_block;   /* sweeps fused per launch by the streaming kernel; 0 = auto */
+    int32_t ghost_top;        /* ghost rows above the slab: 0 = global top edge (border rule applies) */
+    int32_t ghost_bottom;     /* ghost rows below the slab: 0 = global bottom edge */
+    int32_t reserved;
+    double dt;                /* update_step_size */
+    double tension;           /* CCST */
+    double epsilon;           /* TV */
+    double relaxation;        /* 0 or (1,2]: over-relaxation (fd_pde_inpainter.py:317-318) */
+    double term_thres;
+    int64_t term_check_iters;
+    int64_t max_iters;
+} hmi_params;
+
+typedef struct hmi_status {
+    int64_t updates_done;     /* sweeps executed; the reference only prints this */
+    double last_diff;         /* value of the last convergence measure (100000 before any check) */
+    int32_t converged;        /* 1 if a check passed (the reference returns), 0 = max_iters reached */
+    int32_t checks;           /* number of convergence checks evaluated */
+} hmi_status;
+
+/* Partial convergence sums of one slab, for the multi-GPU all-reduce:
+ * sum (fnew-f)^2, sum fnew^2 (ncclSum) and max|fnew-f|, NaN flag (ncclMax). */
+typedef struct hmi_norm {
+    double sum_d2, sum_f2, max_abs, has_nan;
+} hmi_norm;
+
+int hmi_abi_version(void);
+const char *hmi_last_error(void);
+
+/* Number of CUDA devices visible, or a negative hmi_error. */
+int hmi_device_count(void);
+
+/* Create / destroy a solver for one grid (or one row slab of it).  Allocates the two ping-pong
+ * grids, the mask and the reduction scratch on `device`.
+ * Replaces: FDPDEInpainter.__init__ state + the arrays inpaint_grid() allocates per call
+ * (fd_pde_inpainter.py:281-309). */
+int hmi_create(const hmi_params *params, hmi_solver **out);
+void hmi_destroy(hmi_solver *s);
+
+/* Load the *initialised* grid (unknown cells already filled by the initialiser; known cells are
+ * what update_at_mask re-imposes every sweep, update_at_mask.py:6-14) and the mask
+ * (1 byte per cell, non-zero = known).  Arrays cover ghost_top + rows + ghost_bottom rows, dense
+ * row-major with the given row pitches in BYTES.  _host copies from host memory (pageable or
+ * pinned) inside the call; _device reads device pointers on `stream` (a cudaStream_t, NULL = default).
+ * Replaces: `f = image`, `mask_inv = 1 - mask` (fd_pde_inpainter.py:291-303). */
+int hmi_set_problem_host(hmi_solver *s, const void *image, size_t image_pitch_bytes,
+                         const uint8_t *mask, size_t mask_pitch_bytes);
+int hmi_set_problem_device(hmi_solver *s, const void *image_dev, size_t image_pitch_bytes,
+                           const uint8_t *mask_dev, size_t mask_pitch_bytes, void *stream);
+
+/* n raw relaxation sweeps f <- Pi(f + dt*step(f)) without convergence checks, asynchronous on
+ * `stream`.  Replaces n iterations of the loop body fd_pde_inpainter.py:311-326 between checks. */
+int hmi_sweeps(hmi_solver *s, int64_t n, void *stream);
+
+/* n sweeps (n >= 1); the convergence sums between the last two iterates are reduced on the device,
+ * fused into the last sweep, and returned (synchronises `stream`).
+ * Replaces: the loop body + term_check() on a check iteration (fd_pde_inpainter.py:322-323, 368-379). */
+int hmi_sweeps_norm(hmi_solver *s, int64_t n, void *stream, hmi_norm *out);
+
+/* The whole reference loop on one GPU: checks at i % term_check_iters == 0, returns after i+1
+ * updates when a check passes, else after max_iters (status->converged = 0; the reference prints a
+ * warning).  Replaces: FDPDEInpainter.inpaint_grid  fd_pde_inpainter.py:281-366. */
+int hmi_run(hmi_solver *s, void *stream, hmi_status *status);
+
+/* Copy the current iterate (interior rows only) out.  _host synchronises. */
+int hmi_get_result_host(hmi_solver *s, void *out, size_t out_pitch_bytes);
+int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, void *stream);
+
+/* One-shot convenience over host buffers: create + set_problem_host + run + get_result_host +
+ * destroy; host<->device copies happen inside.  This is the end-to-end call bench.py times.
+ * Replaces: FDPDEInpainter.inpaint_grid(image, mask) called with NumPy arrays. */
+int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
+                     hmi_status *status);
+
+/* Multi-GPU plumbing: device address and row pitch (bytes) of the current iterate and of the mask,
+ * so the host layer can exchange ghost rows with NCCL (row 0 = first ghost row).  The addresses
+ * change after every hmi_sweeps*() call (ping-pong). */
+int hmi_current_grid(hmi_solver *s, void **grid_dev, size_t *pitch_bytes);
+int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes);
+
+/* Host-side initialiser helpers (multi-threaded): image[i] = value where mask[i] == 0, and the mean
+ * of the known cells.  Replaces: Initializer.initialize 'zeros' / 'mean', inpainting/initializer.py:15-18
+ * (in place on the caller's host array, as the reference does). */
+int hmi_host_fill_unknown(void *image, const uint8_t *mask, int64_t n, int32_t dtype, double value);
+int hmi_host_known_mean(const void *image, const uint8_t *mask, int64_t n, int32_t dtype, double *mean);
+
+/* Tuning knobs for tests and benchmarks: "chunk_rows" (rows per warp chunk of the streaming kernel,
+ * 0 = auto) and "temporal_block" (sweeps fused per launch). */
+int hmi_set_option(hmi_solver *s, const char *key, int64_t value);
+
+/* Introspection for tests and bench: sweeps fused per launch, kernels launched so far, and the
+ * name of the kernel family the solver selected ("generic", "stream"). */
+int hmi_temporal_block(const hmi_solver *s);
+int64_t hmi_launch_count(const hmi_solver *s);
+const char *hmi_kernel_name(const hmi_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMI_B200_H */

@@ -44,22 +44,32 @@
 static void FN(conv3x3)(const T *img, T *out, int rows, int cols, const double k[9],
                         int orient, int border, const uint8_t *work)
 {
+    /* non-zero taps in the row-major order the numba kernel visits them */
+    int nt = 0, ta[9], tb[9];
+    double tw[9];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            const double w = (orient > 0) ? k[a * 3 + b] : k[(2 - a) * 3 + (2 - b)];
+            if (w == 0.0) continue;
+            ta[nt] = a - 1; tb[nt] = b - 1; tw[nt] = w; ++nt;
+        }
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < rows; ++i) {
+        const int row_inner = (i > 0 && i < rows - 1);
         for (int j = 0; j < cols; ++j) {
             const size_t o = (size_t)i * cols + j;
             if (work && !work[o]) { out[o] = img[o]; continue; }
             double num = 0.0;
-            for (int a = 0; a < 3; ++a) {
-                for (int b = 0; b < 3; ++b) {
-                    const double w = (orient > 0) ? k[a * 3 + b] : k[(2 - a) * 3 + (2 - b)];
-                    if (w == 0.0) continue;
-                    int ii = i - 1 + a, jj = j - 1 + b;
+            if (row_inner && j > 0 && j < cols - 1) {
+                for (int t = 0; t < nt; ++t)
+                    num += tw[t] * (double)img[o + (ptrdiff_t)ta[t] * cols + tb[t]];
+            } else {
+                for (int t = 0; t < nt; ++t) {
                     int inside = 1;
-                    ii = fold_index(ii, rows, border, &inside);
-                    jj = fold_index(jj, cols, border, &inside);
+                    const int ii = fold_index(i + ta[t], rows, border, &inside);
+                    const int jj = fold_index(j + tb[t], cols, border, &inside);
                     if (!inside) continue; /* zero padding */
-                    num += w * (double)img[(size_t)ii * cols + jj];
+                    num += tw[t] * (double)img[(size_t)ii * cols + jj];
                 }
             }
             out[o] = (T)num;

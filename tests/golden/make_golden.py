@@ -186,6 +186,21 @@ def main():
         print(meta[-1])
     out["meta"] = np.array(meta)
     np.savez_compressed(os.path.join(HERE, "converged.npz"), **out)
+
+    # ---------------------------------------------------------------- D. progress table (stdout)
+    import contextlib
+    import io
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run_reference(classes["harmonic"], out["image__f64"], mask, convolver="opencv",
+                      update_step_size=0.2, term_criteria="relative", term_thres=1e-5,
+                      term_check_iters=10, print_progress=True, print_progress_iters=7)
+        run_reference(classes["harmonic"], out["image__f64"], mask, convolver="opencv",
+                      update_step_size=0.2, term_criteria="relative", term_thres=1e-9,
+                      term_check_iters=10, print_progress=True, print_progress_iters=4,
+                      max_iters=23)
+    with open(os.path.join(HERE, "progress_stdout.txt"), "w") as fh:
+        fh.write(buf.getvalue())
     print("golden fixtures written to", HERE)
 
 

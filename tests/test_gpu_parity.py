@@ -1,0 +1,294 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and against the
+golden fixtures produced by the unmodified reference.
+
+Bars (BASELINE.json north_star / SURVEY.md 8d): known cells bit-exact; filled cells within
+1e-10 (fp64) / 1e-5 (fp32) of the reference, measured as max|diff| / (max - min), at the same
+iteration count.  The generic kernel restates the reference's expression order, so against the
+oracle it is held to a far tighter bound.
+"""
+import numpy as np
+import pytest
+
+from helpers import DTYPES, METHOD_OPTS, TOL, parse_converged_meta, range_err
+from oracle.fdpde_oracle import OracleInpainter
+
+import heightmap_interpolation_b200 as hmi
+from heightmap_interpolation_b200 import _capi as C
+from heightmap_interpolation_b200 import synthetic
+from heightmap_interpolation_b200.solver import Solver, make_params
+
+pytestmark = pytest.mark.gpu
+
+METHODS = {"harmonic": C.HMI_HARMONIC, "ccst": C.HMI_CCST, "tv": C.HMI_TV, "amle": C.HMI_AMLE}
+CLASSES = {"harmonic": hmi.SobolevInpainter, "ccst": hmi.CCSTInpainter, "tv": hmi.TVInpainter,
+           "amle": hmi.AMLEInpainter}
+CONV = {"opencv": (1, C.HMI_BORDER_REFLECT101), "masked": (-1, C.HMI_BORDER_REFLECT101),
+        "scipy-signal": (-1, C.HMI_BORDER_ZERO), "scipy-ndimage": (-1, C.HMI_BORDER_ZERO)}
+
+
+def gpu_sweeps(method, conv, image, mask, K, kernel="auto", tb=0, chunk_rows=0, relaxation=0.0,
+               opts=None, want_norm=False):
+    opts = dict(METHOD_OPTS[method]) if opts is None else opts
+    o, b = CONV[conv]
+    p = make_params(image.shape[0], image.shape[1], image.dtype, METHODS[method], orientation=o,
+                    border=b, dt=opts["update_step_size"], tension=opts.get("tension", 0.0),
+                    epsilon=opts.get("epsilon", 1e-2), relaxation=relaxation,
+                    kernel=C.KERNELS[kernel], temporal_block=tb)
+    with Solver(p) as s:
+        if chunk_rows:
+            s.set_option("chunk_rows", chunk_rows)
+        s.set_problem_host(image, mask)
+        nm = None
+        if want_norm:
+            nm = s.sweeps_norm(K)
+        else:
+            s.sweeps(K)
+        out = s.get_result_host()
+        info = (s.kernel_name, s.temporal_block, s.launch_count)
+    return (out, nm, info) if want_norm else (out, info)
+
+
+def oracle_sweeps(method, conv, image, mask, K, **extra):
+    o = OracleInpainter(method, convolver=conv, max_iters=K, term_thres=1e-300,
+                        term_check_iters=10 ** 9, **dict(METHOD_OPTS[method], **extra))
+    return o.inpaint_grid(image.copy(), mask)
+
+
+# ------------------------------------------------------------------ generic kernel == oracle
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("conv", ["opencv", "masked", "scipy-signal"])
+@pytest.mark.parametrize("method", list(METHODS))
+def test_generic_kernel_matches_oracle_tightly(golden_sweeps, method, conv, dt):
+    img = golden_sweeps["image__" + dt].copy()
+    mask = golden_sweeps["mask"]
+    for K in (1, 13):
+        got, info = gpu_sweeps(method, conv, img, mask, K, kernel="generic")
+        assert info[0] == "generic" and info[2] == K
+        ref = oracle_sweeps(method, conv, img, mask, K)
+        assert np.array_equal(got[mask], img[mask])
+        assert range_err(got, ref) <= (1e-14 if dt == "f64" else 1e-7), (method, conv, dt, K)
+
+
+@pytest.mark.parametrize("method", ["tv", "amle"])
+def test_generic_kernel_bit_exact_for_order_preserving_methods(golden_sweeps, method):
+    """TV and AMLE have no 3-or-more-term sums: same expression order => same bits (fp64)."""
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    got, _ = gpu_sweeps(method, "opencv", img, mask, 5, kernel="generic")
+    assert np.array_equal(got, oracle_sweeps(method, "opencv", img, mask, 5))
+
+
+# ------------------------------------------------------------------ CUDA path vs the reference's outputs
+@pytest.mark.parametrize("K", [1, 10, 60])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("conv", ["opencv", "masked"])
+@pytest.mark.parametrize("method", list(METHODS))
+def test_k_sweeps_match_reference_fixtures(golden_sweeps, method, conv, dt, K):
+    img = golden_sweeps["image__" + dt].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__%s__%s__%s__%d" % (method, conv, dt, K)]
+    for kernel in ("generic", "auto"):
+        got, info = gpu_sweeps(method, conv, img, mask, K, kernel=kernel)
+        assert got.dtype == ref.dtype
+        assert np.array_equal(got[mask], ref[mask]), (kernel, info)
+        assert range_err(got, ref) <= TOL[dt], (kernel, info, range_err(got, ref))
+
+
+@pytest.mark.parametrize("conv", ["scipy-ndimage", "scipy-signal"])
+@pytest.mark.parametrize("method", list(METHODS))
+def test_zero_padding_convolvers_match_reference(golden_sweeps, method, conv):
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__%s__%s__f64__10" % (method, conv)]
+    got, _ = gpu_sweeps(method, conv, img, mask, 10)
+    assert range_err(got, ref) <= TOL["f64"]
+
+
+def test_ccst_tension_end_points_and_relaxation(golden_sweeps):
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    for t in (0, 1):
+        ref = golden_sweeps["sweeps__ccst_t%d__opencv__f64__10" % t]
+        for kernel in ("generic", "auto"):
+            got, _ = gpu_sweeps("ccst", "opencv", img, mask, 10, kernel=kernel,
+                                opts={"update_step_size": 0.01, "tension": float(t)})
+            assert range_err(got, ref) <= TOL["f64"]
+    ref = golden_sweeps["sweeps__harmonic_relax15__opencv__f64__10"]
+    got, info = gpu_sweeps("harmonic", "opencv", img, mask, 10, relaxation=1.5)
+    assert info[0] == "generic"           # over-relaxation is served by the generic kernel
+    assert np.array_equal(got[mask], ref[mask])
+    assert range_err(got, ref) <= TOL["f64"]
+
+
+def test_converged_runs_match_reference_through_public_api(golden_converged):
+    """Inpainter(**options).inpaint(image, mask): same stop iteration, last diff, known cells, values."""
+    mask = golden_converged["mask"]
+    for c in parse_converged_meta(golden_converged):
+        img = golden_converged["image__" + c["dtype"]].copy()
+        opts = dict(METHOD_OPTS[c["method"]])
+        opts.update(convolver=c["convolver"], term_criteria=c["criteria"], term_thres=c["thres"],
+                    term_check_iters=c["T"])
+        opts.update(c["extra"])
+        inp = CLASSES[c["method"]](**opts)
+        caller_image = img.copy()
+        got = inp.inpaint(caller_image, mask)
+        ref = golden_converged[c["key"]]
+        assert got.dtype == ref.dtype and got is not caller_image
+        assert inp.iterations_ == c["updates"], (c, inp.iterations_, inp.last_diff_)
+        assert inp.converged_ == c["converged"], c
+        assert inp.last_diff_ == pytest.approx(c["diff"], rel=1e-3 if c["dtype"] == "f32" else 1e-6), c
+        assert float(inp.term_thres) == pytest.approx(c["final_thres"], rel=1e-6), c
+        assert np.array_equal(got[mask], ref[mask]), c
+        assert range_err(got, ref) <= TOL[c["dtype"]], (c, range_err(got, ref))
+        if c["extra"].get("init_with") == "mean":     # caller's array initialised in place
+            assert caller_image[~mask][0] == pytest.approx(img[mask].mean())
+
+
+# ------------------------------------------------------------------ streaming kernel vs oracle
+def _problem(rows, cols, dtype, p=0.4, seed=3):
+    img = synthetic.bathymetry((rows, cols), seed=7, dtype=dtype)
+    mask = synthetic.mask_random((rows, cols), p, seed=seed)
+    mask[0, 0] = mask[0, -1] = mask[-1, 0] = mask[-1, -1] = False
+    mask[0, 5:40] = False
+    mask[-1, 3:30] = False
+    mask[10:60, 0] = False
+    mask[20:90, -1] = False
+    return synthetic.zero_unknown(img, mask), mask
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("method,tb", [("harmonic", 1), ("harmonic", 2), ("harmonic", 3),
+                                       ("harmonic", 4), ("harmonic", 5), ("harmonic", 8),
+                                       ("ccst", 1), ("ccst", 2), ("ccst", 3), ("ccst", 4)])
+def test_stream_kernel_matches_oracle(method, tb, dt):
+    # odd sizes: ragged last strip, last chunk, columns not a multiple of the vector width
+    img, mask = _problem(211, 333, DTYPES[dt])
+    K = 2 * tb + 1                                    # two full blocks + a remainder block
+    got, info = gpu_sweeps(method, "opencv", img, mask, K, kernel="stream", tb=tb, chunk_rows=37)
+    assert info[0] == "stream" and info[1] == tb
+    ref = oracle_sweeps(method, "opencv", img, mask, K)
+    assert np.array_equal(got[mask], img[mask])
+    err = range_err(got, ref)
+    assert err <= (1e-13 if dt == "f64" else 2e-6), (method, tb, dt, err)
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (130, 120), (97, 1031), (1031, 97), (512, 512)])
+def test_stream_kernel_shapes_and_chunking(shape):
+    img, mask = _problem(shape[0], shape[1], np.float64)
+    ref = oracle_sweeps("ccst", "masked", img, mask, 6)
+    for chunk in (0, 8, 50, 10 ** 6):
+        got, info = gpu_sweeps("ccst", "masked", img, mask, 6, kernel="stream", tb=2, chunk_rows=chunk)
+        assert range_err(got, ref) <= 1e-13, (shape, chunk)
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("method", ["harmonic", "ccst", "tv", "amle"])
+def test_fused_norm_matches_oracle(method, dt):
+    img, mask = _problem(150, 260, DTYPES[dt])
+    K = 7
+    prev = oracle_sweeps(method, "opencv", img, mask, K - 1)
+    last = oracle_sweeps(method, "opencv", img, mask, K)
+    d = last.astype(np.float64) - prev.astype(np.float64)
+    for kernel in ("generic", "auto"):
+        got, nm, info = gpu_sweeps(method, "opencv", img, mask, K, kernel=kernel, want_norm=True)
+        rel = 1e-9 if dt == "f64" else 1e-3
+        assert nm.sum_d2 == pytest.approx(float(np.sum(d * d)), rel=rel), (kernel, info)
+        assert nm.sum_f2 == pytest.approx(float(np.sum(last.astype(np.float64) ** 2)), rel=rel)
+        assert nm.max_abs == pytest.approx(float(np.abs(d).max()), rel=rel)
+        assert nm.has_nan == 0.0
+
+
+def test_nan_never_converges_and_all_known_grid_is_identity():
+    img = np.zeros((40, 50))
+    mask = np.ones((40, 50), dtype=bool)
+    mask[5:9, 5:9] = False                     # all-zero grid: relative criterion is 0/0 = NaN
+    inp = hmi.SobolevInpainter(update_step_size=0.2, term_check_iters=5, max_iters=20)
+    out = inp.inpaint(img.copy(), mask)
+    assert not inp.converged_ and inp.iterations_ == 20 and np.isnan(inp.last_diff_)
+    assert np.array_equal(out, img)
+    img, _ = _problem(70, 90, np.float32)
+    allk = np.ones(img.shape, dtype=bool)
+    inp = hmi.CCSTInpainter(update_step_size=0.01, tension=0.3, term_check_iters=3, max_iters=9)
+    out = inp.inpaint(img.copy(), allk)
+    assert np.array_equal(out, img) and inp.converged_ and inp.iterations_ == 1
+
+
+# ------------------------------------------------------------------ slabs with ghost rows (multi-GPU data path on one GPU)
+@pytest.mark.parametrize("method,kernel,block", [("harmonic", "stream", 4), ("ccst", "stream", 2),
+                                                 ("tv", "generic", 3), ("amle", "generic", 2),
+                                                 ("ccst", "generic", 2)])
+def test_two_slabs_with_halo_exchange_equal_one_grid(method, kernel, block):
+    """Row-slab decomposition: two solvers with ghost rows, halos copied by the test between
+    temporal blocks, must reproduce the single-grid result exactly (same kernels, same order)."""
+    rows, cols = 160, 200
+    img, mask = _problem(rows, cols, np.float64)
+    opts = METHOD_OPTS[method]
+    rad = 2 if method == "ccst" else 1
+    G = rad * block
+    nblocks = 3
+    whole, _ = gpu_sweeps(method, "opencv", img, mask, block * nblocks, kernel=kernel, tb=block)
+
+    split = 70
+    def mk(r0, r1, gt, gb):
+        p = make_params(r1 - r0, cols, np.float64, METHODS[method], orientation=1, dt=opts["update_step_size"],
+                        tension=opts.get("tension", 0.0), epsilon=opts.get("epsilon", 1e-2),
+                        kernel=C.KERNELS[kernel], temporal_block=block, ghost_top=gt, ghost_bottom=gb)
+        s = Solver(p)
+        s.set_problem_host(img[r0 - gt:r1 + gb], mask[r0 - gt:r1 + gb])
+        return s
+    top, bot = mk(0, split, 0, G), mk(split, rows, G, 0)
+    for b in range(nblocks):
+        if b > 0:   # refresh the halos: G rows across the seam, through the host
+            cur = np.vstack([top.get_result_host(), bot.get_result_host()])
+            top.set_problem_host(cur[0:split + G], mask[0:split + G])
+            bot.set_problem_host(cur[split - G:rows], mask[split - G:rows])
+        top.sweeps(block)
+        bot.sweeps(block)
+    got = np.vstack([top.get_result_host(), bot.get_result_host()])
+    top.close(); bot.close()
+    assert np.array_equal(got, whole), float(np.abs(got - whole).max())
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_4096():
+    """BASELINE config 2 size (CCST, 4096^2 fp64, survey tracks): size-independent properties —
+    known cells bit-exact, streaming kernel == generic kernel, a cropped corner equals the oracle."""
+    n = 4096
+    img = synthetic.bathymetry(n, seed=7)
+    mask = synthetic.mask_tracks(n, 8, 16, 256)
+    img = synthetic.zero_unknown(img, mask)
+    K = 8
+    fast, info = gpu_sweeps("ccst", "opencv", img, mask, K)
+    assert info[0] == "stream"
+    slow, _ = gpu_sweeps("ccst", "opencv", img, mask, K, kernel="generic")
+    assert np.array_equal(fast[mask], img[mask])
+    assert range_err(fast, slow) <= 1e-13
+    # the corner block depends only on cells within 2*K of it
+    c = 96
+    ref = oracle_sweeps("ccst", "opencv", img[:c + 2 * K + 2, :c + 2 * K + 2],
+                        mask[:c + 2 * K + 2, :c + 2 * K + 2], K)
+    assert range_err(fast[:c, :c], ref[:c, :c]) <= 1e-12
+    ref = oracle_sweeps("ccst", "opencv", img[-(c + 2 * K + 2):, -(c + 2 * K + 2):],
+                        mask[-(c + 2 * K + 2):, -(c + 2 * K + 2):], K)
+    assert range_err(fast[-c:, -c:], ref[-c:, -c:]) <= 1e-12
+
+
+def test_full_size_properties_8192_fp32_tv():
+    """BASELINE config 3 size (TV, 8192^2 fp32, large holes): known cells exact; a hole-containing
+    window matches the oracle run on the window plus its dependency margin."""
+    n = 8192
+    img = synthetic.gaussian_hill(n, dtype=np.float32)
+    mask = synthetic.mask_holes(n, 64, 32, seed=1)
+    img = synthetic.zero_unknown(img, mask)
+    K = 4
+    got, info = gpu_sweeps("tv", "opencv", img, mask, K)
+    assert np.array_equal(got[mask], img[mask])
+    ys, xs = np.nonzero(~mask)
+    y0, x0 = int(ys[0]), int(xs[0])
+    m = K + 2
+    ya, yb, xa, xb = max(0, y0 - 40), min(n, y0 + 40), max(0, x0 - 40), min(n, x0 + 40)
+    Ya, Yb, Xa, Xb = max(0, ya - m), min(n, yb + m), max(0, xa - m), min(n, xb + m)
+    ref = oracle_sweeps("tv", "opencv", img[Ya:Yb, Xa:Xb], mask[Ya:Yb, Xa:Xb], K)
+    sub = ref[ya - Ya:ya - Ya + (yb - ya), xa - Xa:xa - Xa + (xb - xa)]
+    if Ya > 0 and Xa > 0 and Yb < n and Xb < n:     # window away from the global border
+        assert range_err(got[ya:yb, xa:xb], sub) <= TOL["f32"]

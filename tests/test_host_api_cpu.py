@@ -1,0 +1,245 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports what include/hmi_b200.h declares,
+the reference-facing Python layer keeps the reference's options / defaults / errors, and the
+event-driven host loop reproduces the reference's check cadence and progress table."""
+import argparse
+import contextlib
+import ctypes
+import io
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from helpers import METHOD_OPTS
+from oracle.fdpde_oracle import OracleInpainter
+
+import heightmap_interpolation_b200 as hmi
+from heightmap_interpolation_b200 import _capi as C
+from heightmap_interpolation_b200.apps.apps_common import create_inpainter_from_params
+from heightmap_interpolation_b200.solver import Norm, make_params
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hmi_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hmi_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(C.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export " + name
+    assert declared == set(C.SYMBOLS), declared ^ set(C.SYMBOLS)
+    assert C.lib().hmi_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header():
+    # 14 int32 + 5 double + 2 int64
+    assert ctypes.sizeof(C.HmiParams) == 14 * 4 + 5 * 8 + 2 * 8
+    p = make_params(8, 8, np.float64, C.HMI_HARMONIC)
+    assert p.struct_size == ctypes.sizeof(C.HmiParams)
+
+
+def test_create_rejects_bad_arguments_before_touching_the_gpu():
+    lib = C.lib()
+    h = ctypes.c_void_p()
+    p = make_params(8, 8, np.float64, C.HMI_HARMONIC, dt=0.2)
+    p.struct_size = 4
+    assert lib.hmi_create(ctypes.byref(p), ctypes.byref(h)) == C.HMI_ERR_BAD_ARG
+    for bad in (dict(rows=1), dict(dt=0.0), dict(term_thres=-1.0), dict(max_iters=0),
+                dict(relaxation=0.5), dict(relaxation=2.5), dict(term_check_iters=0)):
+        kw = dict(rows=8, cols=8, dtype=np.float64, method=C.HMI_HARMONIC, dt=0.2)
+        kw.update(bad)
+        p = make_params(**kw)
+        assert lib.hmi_create(ctypes.byref(p), ctypes.byref(h)) == C.HMI_ERR_BAD_ARG, bad
+        assert lib.hmi_last_error()
+    p = make_params(8, 8, np.float64, C.HMI_CCST, dt=0.01, tension=1.5)
+    assert lib.hmi_create(ctypes.byref(p), ctypes.byref(h)) == C.HMI_ERR_BAD_ARG
+    assert b"tension" in lib.hmi_last_error()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    inp = hmi.SobolevInpainter(update_step_size=0.2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        inp.inpaint(np.zeros((8, 8)), np.ones((8, 8), dtype=bool))
+
+
+def test_constructor_defaults_and_get_config_match_reference():
+    inp = hmi.SobolevInpainter()
+    assert inp.get_config() == {
+        "update_step_size": 0.01, "term_criteria": "relative", "term_check_iters": 1000,
+        "term_thres": 1e-8, "max_iters": int(1e8), "relaxation": 0, "print_progress": False,
+        "print_progress_iters": 1000, "mgs_levels": 1, "mgs_min_res": 100, "init_with": "zeros",
+        "convolver": "masked"}
+    assert hmi.CCSTInpainter(tension=0.3).get_config()["tension"] == 0.3
+    assert hmi.CCSTInpainter().get_config()["tension"] == 0.0
+    assert hmi.TVInpainter().get_config()["epsilon"] == 1e-2
+    assert "tension" not in hmi.AMLEInpainter().get_config()
+    # unknown keywords are silently ignored, like the reference
+    hmi.SobolevInpainter(backend="gpu", ti_arch="cuda", bogus=1)
+    # floats are accepted for max_iters and truncated
+    assert hmi.SobolevInpainter(max_iters=1e5).max_iters == 100000
+
+
+@pytest.mark.parametrize("cls,kw,msg", [
+    (hmi.SobolevInpainter, dict(update_step_size=0), "update_step_size must be larger than zero"),
+    (hmi.SobolevInpainter, dict(term_thres=0), "term_thres must be larger than zero"),
+    (hmi.SobolevInpainter, dict(max_iters=0), "max_iters must be larger than zero"),
+    (hmi.SobolevInpainter, dict(relaxation=0.5), "relaxation must be a number between 1 and 2"),
+    (hmi.SobolevInpainter, dict(relaxation=2.1), "relaxation must be a number between 1 and 2"),
+    (hmi.SobolevInpainter, dict(mgs_levels=2.0), "mgs_levels must be an integer"),
+    (hmi.SobolevInpainter, dict(mgs_min_res=10.5), "mgs_min_res must be an integer"),
+    (hmi.SobolevInpainter, dict(init_with="harmonic"), "init_with must be one of these options"),
+    (hmi.SobolevInpainter, dict(convolver="numpy"), "Unknown convolver type 'numpy'"),
+    (hmi.CCSTInpainter, dict(tension=-0.1), "tension parameter must be a number between 0 and 1"),
+    (hmi.CCSTInpainter, dict(tension=1.1), "tension parameter must be a number between 0 and 1"),
+    (hmi.TVInpainter, dict(epsilon=0), "Epsilon parameter must be greater than zero"),
+])
+def test_constructor_validation_errors(cls, kw, msg):
+    with pytest.raises(ValueError, match=msg):
+        cls(**kw)
+
+
+def test_unknown_term_criteria_raises_at_solve_time():
+    inp = hmi.SobolevInpainter(term_criteria="bogus")       # accepted by the constructor
+    with pytest.raises(ValueError, match="Unknown termination criteria!"):
+        inp.set_term_criteria(np.zeros((4, 4)))
+
+
+def test_absolute_percent_scales_threshold_in_place_and_compounds():
+    inp = hmi.SobolevInpainter(term_criteria="absolute_percent", term_thres=1e-5)
+    f = np.array([[0.0, 100.0], [50.0, 25.0]])
+    inp.set_term_criteria(f)
+    assert inp.term_thres == pytest.approx(1e-3)
+    inp.set_term_criteria(f)                                   # the reference compounds on re-use
+    assert inp.term_thres == pytest.approx(1e-1)
+
+
+def test_convolver_names_map_to_orientation_and_border():
+    tab = {n: (hmi.SobolevInpainter(convolver=n).convolver.orientation,
+               hmi.SobolevInpainter(convolver=n).convolver.border)
+           for n in ("opencv", "masked", "masked-parallel", "scipy-signal", "scipy-ndimage")}
+    assert tab["opencv"] == (1, C.HMI_BORDER_REFLECT101)
+    assert tab["masked"] == tab["masked-parallel"] == (-1, C.HMI_BORDER_REFLECT101)
+    assert tab["scipy-signal"] == tab["scipy-ndimage"] == (-1, C.HMI_BORDER_ZERO)
+
+
+def test_cli_dispatch_names():
+    def ns(name, **kw):
+        base = dict(subparser_name=name, update_step_size=0.2, term_thres=1e-5, verbose=False)
+        base.update(kw)
+        return argparse.Namespace(**base)
+    assert isinstance(create_inpainter_from_params(ns("harmonic")), hmi.SobolevInpainter)
+    tv = create_inpainter_from_params(ns("tv", epsilon=1.0))
+    assert isinstance(tv, hmi.TVInpainter) and tv.epsilon == 1.0
+    cc = create_inpainter_from_params(ns("ccst", tension=0.3))
+    assert isinstance(cc, hmi.CCSTInpainter) and cc.tension == 0.3
+    assert isinstance(create_inpainter_from_params(ns("ccst-ti", tension=0.1)), hmi.CCSTInpainter)
+    assert isinstance(create_inpainter_from_params(ns("amle")), hmi.AMLEInpainter)
+    # CLI defaults of the reference (apps_common.py:38-53)
+    h = create_inpainter_from_params(ns("harmonic"))
+    assert (h.term_criteria, h.init_with, h.convolver_type, h.max_iters) == \
+        ("absolute_percent", "nearest", "opencv", 1000000)
+    with pytest.raises(ValueError):
+        create_inpainter_from_params(ns("telea"))
+
+
+def test_initializers_zeros_and_mean_in_place():
+    img = np.arange(12, dtype=np.float64).reshape(3, 4)
+    mask = np.ones((3, 4), dtype=bool)
+    mask[1, 1] = mask[2, 3] = False
+    a = img.copy()
+    out = hmi.SobolevInpainter(init_with="zeros").initializer.initialize(a, mask)
+    assert out is a and a[1, 1] == 0 and a[2, 3] == 0
+    b = img.copy()
+    hmi.SobolevInpainter(init_with="mean").initializer.initialize(b, mask)
+    assert b[1, 1] == pytest.approx(img[mask].mean())
+
+
+class OracleEngine:
+    """Stand-in for the CUDA solver in host-logic tests: same sweeps()/sweeps_norm() surface,
+    arithmetic by the CPU oracle (test infrastructure)."""
+
+    def __init__(self, method, image, mask, **opts):
+        self.f = image.copy()
+        self.mask = mask
+        self.o = lambda k: OracleInpainter(method, max_iters=k, term_thres=1e-300,
+                                           term_check_iters=10 ** 9, **opts)
+        self.calls = []
+
+    def sweeps(self, n):
+        self.calls.append(("sweeps", n))
+        if n > 0:
+            self.f = self.o(n).inpaint_grid(self.f, self.mask)
+
+    def sweeps_norm(self, n):
+        self.calls.append(("norm", n))
+        if n > 1:
+            self.f = self.o(n - 1).inpaint_grid(self.f, self.mask)
+        fnew = self.o(1).inpaint_grid(self.f, self.mask)
+        d = fnew - self.f
+        nm = Norm(float(np.sum(d * d)), float(np.sum(fnew * fnew)), float(np.abs(d).max()), 0.0)
+        self.f = fnew
+        return nm
+
+
+def test_host_loop_reproduces_reference_progress_table_and_stop_iteration(golden_converged):
+    mask = golden_converged["mask"]
+    img = golden_converged["image__f64"].copy()
+    img[~mask] = 0
+    expected = open(os.path.join(GOLDEN, "progress_stdout.txt")).read()
+
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        for thres, P, extra in ((1e-5, 7, {}), (1e-9, 4, {"max_iters": 23})):
+            inp = hmi.SobolevInpainter(update_step_size=0.2, convolver="opencv", term_thres=thres,
+                                       term_check_iters=10, print_progress=True,
+                                       print_progress_iters=P, **extra)
+            inp.print_msg("*** INPAINTING ***")
+            inp.print_msg("* Initializing the inpainting problem using the 'zeros' filler")
+            inp.print_msg("* Optimization:")
+            inp.set_term_criteria(img)
+            eng = OracleEngine("harmonic", img, mask, update_step_size=0.2, convolver="opencv")
+            done, diff, conv = inp._loop(eng, C.HMI_RELATIVE)
+            if not conv:
+                print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
+            if not extra:
+                assert (done, conv) == (51, True)
+                assert np.allclose(eng.f, golden_converged["conv00"], rtol=0, atol=1e-9)
+            else:
+                assert (done, conv) == (23, False)
+    assert buf.getvalue() == expected
+
+
+def test_host_loop_check_cadence():
+    """Checks fall on i % T == 0; returns after i+1 updates; no check when max_iters comes first."""
+    class Fake:
+        def __init__(self, converge_at):
+            self.n = 0
+            self.converge_at = converge_at
+            self.log = []
+
+        def sweeps(self, n):
+            self.n += n
+            self.log.append(("s", n))
+
+        def sweeps_norm(self, n):
+            self.n += n
+            self.log.append(("n", n))
+            return Norm(0.0 if self.n >= self.converge_at else 1.0, 1.0, 0.0, 0.0)
+
+    inp = hmi.SobolevInpainter(term_check_iters=1000, term_thres=1e-5)
+    f = Fake(converge_at=500)
+    assert inp._loop(f, C.HMI_RELATIVE) == (1001, 0.0, True)
+    assert f.log == [("n", 1), ("n", 1000)]
+    inp = hmi.SobolevInpainter(term_check_iters=7, term_thres=1e-5, max_iters=20)
+    f = Fake(converge_at=10 ** 9)
+    done, diff, conv = inp._loop(f, C.HMI_RELATIVE)
+    assert (done, conv) == (20, False)
+    assert f.log == [("n", 1), ("n", 7), ("n", 7), ("s", 5)]
+    # NaN never terminates (0/0 in the relative criterion)
+    assert not (Norm(0.0, 0.0, 0.0, 0.0).diff(C.HMI_RELATIVE) < 1.0)
+    assert np.isnan(Norm(0.0, 1.0, 3.0, 1.0).diff(C.HMI_ABSOLUTE))
