@@ -33,6 +33,19 @@ int fail(int code, const char *fmt, ...)
 
 long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// The streaming kernel packs four mask bytes with one multiply, which needs them to be exactly 0/1.
+__global__ void normalize_mask_kernel(uint8_t *m, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint32_t *w = reinterpret_cast<uint32_t *>(m);
+    for (size_t q = i; q < n / 4; q += stride) {
+        const uint32_t v = w[q];
+        w[q] = ((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 0x100u : 0u) |
+               ((v & 0xff0000u) ? 0x10000u : 0u) | ((v & 0xff000000u) ? 0x1000000u : 0u);
+    }
+}
+
 }  // namespace
 
 struct hmi_solver {
@@ -340,6 +353,8 @@ int hmi_set_problem_host(hmi_solver *s, const void *image, size_t image_pitch_by
                           s->phys_rows, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy2D(s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
                           s->phys_rows, cudaMemcpyHostToDevice));
+    normalize_mask_kernel<<<592, 256>>>(s->mask, (size_t)s->phys_rows * s->mpitch);
+    CUDA_TRY(cudaGetLastError());
     s->has_problem = true;
     return HMI_OK;
 }
@@ -358,6 +373,8 @@ int hmi_set_problem_device(hmi_solver *s, const void *image_dev, size_t image_pi
                                wbytes, s->phys_rows, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpy2DAsync(s->mask, (size_t)s->mpitch, mask_dev, mask_pitch_bytes,
                                (size_t)s->p.cols, s->phys_rows, cudaMemcpyDeviceToDevice, st));
+    normalize_mask_kernel<<<592, 256, 0, st>>>(s->mask, (size_t)s->phys_rows * s->mpitch);
+    CUDA_TRY(cudaGetLastError());
     s->has_problem = true;
     return HMI_OK;
 }

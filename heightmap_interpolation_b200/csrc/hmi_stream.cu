@@ -4,9 +4,14 @@
 // Design (B200-first, no counterpart in the reference, which runs one full-grid NumPy/OpenCV pass
 // per operator: fd_pde_inpainter.py:311-326):
 //   * One WARP owns a column strip of 32*V cells and streams down a chunk of rows.  Each lane holds
-//     V consecutive cells of the current row in registers (one or two 16-byte loads per lane,
-//     coalesced across the warp); x-neighbours come from warp shuffles, y-neighbours from the
-//     previous rows kept in registers.  No shared memory and no block barrier on the hot loop.
+//     V consecutive cells of the current row in registers; x-neighbours come from warp shuffles,
+//     y-neighbours from the previous rows kept in registers.  No block barrier on the hot loop.
+//   * Rows are staged through a per-warp shared-memory ring filled by asynchronous 16-byte copies
+//     (cp.async / LDGSTS, coalesced: a warp moves one 1 KiB fp64 row segment per copy pair) issued
+//     D-1 rows ahead, so ~D KiB per warp are in flight without holding registers or coupling to
+//     the load scoreboard.  Each lane reads back only what it copied itself, so the ring needs no
+//     barrier either (edge strips, which mirror ghost columns out of other lanes' data, use a
+//     __syncwarp).
 //   * Temporal blocking: K relaxation sweeps are fused as a K-stage software pipeline in
 //     registers.  Row y enters stage 0 as it is loaded; stage s emits sweep s+1 of row y-r(s+1)
 //     (r = stencil radius: 1 harmonic, 2 CCST).  Only the K-th iterate is written back, so HBM
@@ -29,20 +34,6 @@ template <> struct Chunk16<float> { typedef float4 type; static constexpr int N 
 template <> struct Chunk16<double> { typedef double2 type; static constexpr int N = 2; };
 
 template <typename T, int V>
-__device__ __forceinline__ void load_row_vec(const T *__restrict__ p, T (&v)[V])
-{
-    typedef typename Chunk16<T>::type C;
-    constexpr int N = Chunk16<T>::N;
-#pragma unroll
-    for (int c = 0; c < V / N; ++c) {
-        const C t = __ldg(reinterpret_cast<const C *>(p) + c);
-        const T *e = reinterpret_cast<const T *>(&t);
-#pragma unroll
-        for (int q = 0; q < N; ++q) v[c * N + q] = e[q];
-    }
-}
-
-template <typename T, int V>
 __device__ __forceinline__ void store_row_vec(T *__restrict__ p, const T (&v)[V])
 {
     typedef typename Chunk16<T>::type C;
@@ -57,90 +48,65 @@ __device__ __forceinline__ void store_row_vec(T *__restrict__ p, const T (&v)[V]
     }
 }
 
-template <int V>
-__device__ __forceinline__ unsigned load_mask_vec(const uint8_t *__restrict__ p)
+__device__ __forceinline__ unsigned smem_u32(const void *p)
 {
-    // returns V bits, bit v set = cell v is KNOWN
-    unsigned bits = 0;
-    if (V == 4) {
-        const uchar4 m = __ldg(reinterpret_cast<const uchar4 *>(p));
-        bits = (m.x ? 1u : 0u) | (m.y ? 2u : 0u) | (m.z ? 4u : 0u) | (m.w ? 8u : 0u);
-    } else if (V == 2) {
-        const uchar2 m = __ldg(reinterpret_cast<const uchar2 *>(p));
-        bits = (m.x ? 1u : 0u) | (m.y ? 2u : 0u);
-    } else {
-#pragma unroll
-        for (int v = 0; v < V; ++v) bits |= (__ldg(p + v) ? 1u : 0u) << v;
-    }
-    return bits;
+    return (unsigned)__cvta_generic_to_shared(p);
 }
-
-// One loaded row: V values + V mask bits
-template <typename T, int V>
-struct Row {
-    T v[V];
-    unsigned m;
-};
-
-template <typename T, int V>
-__device__ __forceinline__ void load_row(const StreamArgs<T> &a, int y, int col0, bool edge, Row<T, V> &r)
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
 {
-    // row index with the reflect-101 rule at global edges, clamped to the rows that exist
-    int ry = y;
-    if (ry < 0 && a.top_border) ry = -ry;
-    else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
-    ry = max(a.read_lo, min(a.read_hi - 1, ry));
-    const T *prow = a.src + (long long)ry * a.pitch;
-    const uint8_t *mrow = a.mask + (long long)ry * a.mpitch;
-    if (!edge) {
-        load_row_vec<T, V>(prow + col0, r.v);
-        r.m = load_mask_vec<V>(mrow + col0);
-    } else {
-        unsigned bits = 0;
-#pragma unroll
-        for (int q = 0; q < V; ++q) {
-            int c = col0 + q;
-            if (c < 0) c = -c;
-            else if (c >= a.cols) c = 2 * (a.cols - 1) - c;
-            c = max(0, min(a.cols - 1, c));
-            r.v[q] = __ldg(prow + c);
-            bits |= (__ldg(mrow + c) ? 1u : 0u) << q;
-        }
-        r.m = bits;
-    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <typename T>
 __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <typename T>
 __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-// 5-point Laplacian of the centre row b given the rows above/below and b's lane halos
+template <int PH> struct Phase { static constexpr int value = PH; };
+
+// Sum of the four neighbours of centre row b (rows above/below + lane halos)
 template <typename T, int V>
-__device__ __forceinline__ void lap_row(const T (&up)[V], const T (&b)[V], const T (&dn)[V], T bl, T br,
-                                        T (&out)[V])
+__device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], const T (&dn)[V], T bl, T br,
+                                         T (&out)[V])
 {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const T l = (v > 0) ? b[v - 1] : bl;
         const T r = (v < V - 1) ? b[v + 1] : br;
-        out[v] = ((up[v] + l) + (r + dn[v])) - T(4) * b[v];
+        out[v] = (up[v] + l) + (r + dn[v]);
     }
 }
 
-template <typename T, int V, int K, int METHOD, int PF, int WPB, int MINB>
+template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB>
 __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs<T> a)
 {
+    static_assert(V == 4, "the shared-memory ring moves 4 mask bytes per lane");
+    typedef typename Chunk16<T>::type C16;
+    constexpr int N = Chunk16<T>::N;               // cells per 16-byte chunk
+    constexpr int NCH = V / N;                     // 16-byte chunks per lane per row
     constexpr int R = (METHOD == HMI_CCST) ? 2 : 1;
     constexpr int H = K * R;                       // rows/columns of halo one launch consumes
     constexpr int HV = ((H + V - 1) / V) * V;      // column halo rounded to whole lanes
     constexpr int S = 32 * V - 2 * HV;             // columns a warp produces
-    constexpr unsigned VM = (1u << V) - 1u;
+    constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
+    constexpr int SLOT = ROW_BYTES + 32 * V;       // one row segment + its mask bytes
+    constexpr bool CC = (METHOD == HMI_CCST);
     static_assert(S > 0, "temporal block too deep for this strip width");
+    static_assert(D >= 3, "ring too shallow");
 
+    extern __shared__ __align__(16) unsigned char ring_all[];
     __shared__ double sh[128];
     const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * WPB + (threadIdx.x >> 5);
+    const int wib = threadIdx.x >> 5;
+    unsigned char *ring = ring_all + (size_t)wib * D * SLOT;
+    const long long gw = (long long)blockIdx.x * WPB + wib;
     const int win = (int)(gw % a.nwin);
     const int chunk = (int)(gw / a.nwin);
     double n_d2 = 0.0, n_f2 = 0.0, n_mx = 0.0, n_nan = 0.0;
@@ -149,124 +115,174 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
         const int x0 = win * S - HV;
         const int col0 = x0 + lane * V;
         const bool edge = (x0 < 0) || (x0 + 32 * V > a.cols);
+        const bool copies = (col0 >= 0) && (col0 + V <= (int)a.pitch);   // lane's cells exist in memory
         const int y0 = a.row_lo + chunk * a.chunk_rows;
         const int y1 = min(a.row_hi, y0 + a.chunk_rows);
         const bool out_lane = (lane >= HV / V) && (lane < 32 - HV / V) && (col0 < a.cols);
         const T dt = a.dt;
+        // CCST with folded coefficients: f' = f + c2*(sum of h's four neighbours) + c3*h,
+        //   c2 = -dt(1-t), c3 = dt*t - 4*c2      (== f + dt*(t*h - (1-t)*L h))
+        const T c2 = -(dt * a.one_minus_tension);
+        const T c3 = dt * a.tension - T(4) * c2;
 
-        // pipeline state
-        T FA[K][V], FB[K][V], FBL[K], FBR[K];
-        T HA[K][V], HB[K][V], HBL[K], HBR[K];      // CCST only (dead code for harmonic)
+        // Pipeline state.  Stage s keeps a 3-row window of its input field in F[s][0..2]; the row
+        // loop is unrolled by 3 so the window rotates by renaming (no register moves): in phase PH
+        // the rows above / centre / new sit in slots PH, PH+1, PH+2 (mod 3).  Stage s writes its
+        // output row straight into the new-row slot of stage s+1.
+        T F[K + 1][3][V];
+        T Hh[CC ? K : 1][3][V];                    // CCST: window of h = L f
+        T FL[K], FR[K], HL[CC ? K : 1], HR[CC ? K : 1];
         unsigned long long mhist = 0ull;
 #pragma unroll
         for (int s = 0; s < K; ++s) {
-            FBL[s] = FBR[s] = HBL[s] = HBR[s] = T(0);
+            FL[s] = FR[s] = T(0);
+            if (CC) HL[s] = HR[s] = T(0);
 #pragma unroll
-            for (int v = 0; v < V; ++v) { FA[s][v] = FB[s][v] = HA[s][v] = HB[s][v] = T(0); }
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    F[s][q][v] = T(0);
+                    if (CC) Hh[s][q][v] = T(0);
+                }
         }
 
         const int ybeg = y0 - H, yend = y1 + H;    // rows streamed: [ybeg, yend)
-        Row<T, V> pre[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u)
-            if (ybeg + u < yend) load_row<T, V>(a, ybeg + u, col0, edge, pre[u]);
+        const T *gbase = a.src + col0;
+        const uint8_t *mbase = a.mask + col0;
+        const unsigned ring_f = smem_u32(ring) + lane * 16;
+        const unsigned ring_m = smem_u32(ring) + ROW_BYTES + lane * 4;
 
-        for (int yb = ybeg; yb < yend; yb += PF) {
+        // asynchronous copy of row y (reflect-101 at global edges) into ring slot `slot`
+        auto issue = [&](int y, int slot) {
+            if (y < yend && copies) {
+                int ry = y;
+                if (ry < 0 && a.top_border) ry = -ry;
+                else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
+                ry = max(a.read_lo, min(a.read_hi - 1, ry));
+                const T *prow = gbase + (long long)ry * a.pitch;
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const int y = yb + u;
-                if (y < yend) {
-                    T cur[V];
-#pragma unroll
-                    for (int v = 0; v < V; ++v) cur[v] = pre[u].v[v];
-                    mhist = (mhist << V) | (unsigned long long)pre[u].m;
-                    if (y + PF < yend) load_row<T, V>(a, y + PF, col0, edge, pre[u]);
+                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + slot * SLOT + c * 512, prow + c * N);
+                cp_async4(ring_m + slot * SLOT, mbase + (long long)ry * a.mpitch);
+            }
+            cp_async_commit();
+        };
 
 #pragma unroll
-                    for (int s = 0; s < K; ++s) {
-                        T out[V];
-                        if (METHOD == HMI_HARMONIC) {
-                            // centre row FB[s] (row y-s-1), above FA[s], below cur
-                            const unsigned kb = (unsigned)(mhist >> ((s + 1) * V)) & VM;
-                            T lp[V];
-                            lap_row<T, V>(FA[s], FB[s], cur, FBL[s], FBR[s], lp);
+        for (int u = 0; u < D - 1; ++u) issue(ybeg + u, u);
+
+        int slot = 0;
+        auto step = [&](auto ph, const int y) {
+            constexpr int PH = decltype(ph)::value;
+            constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
+            cp_async_wait<D - 2>();                 // row y has landed (this lane's part)
+            if (edge) __syncwarp();                 // ... and every other lane's part
+            const unsigned char *sl = ring + slot * SLOT;
 #pragma unroll
-                            for (int v = 0; v < V; ++v) {
-                                const T c = FB[s][v];
-                                const T cand = c + dt * lp[v];
-                                out[v] = ((kb >> v) & 1u) ? c : cand;
-                            }
-                            if (s == K - 1 && a.do_norm) {
-                                const int yo = y - H;
-                                if (out_lane && yo >= y0 && yo < y1 && yo >= 0 && yo < a.rows) {
+            for (int c = 0; c < NCH; ++c) {
+                const C16 t = *reinterpret_cast<const C16 *>(sl + c * 512 + lane * 16);
+                const T *e = reinterpret_cast<const T *>(&t);
 #pragma unroll
-                                    for (int v = 0; v < V; ++v) {
-                                        if (col0 + v < a.cols) {
-                                            const T d = out[v] - FB[s][v];
-                                            const double dd = (double)d;
-                                            n_d2 += dd * dd;
-                                            n_f2 += (double)out[v] * (double)out[v];
-                                            const double ad = fabs(dd);
-                                            if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
-                                        }
-                                    }
-                                }
-                            }
-                            // shift the window
+                for (int q = 0; q < N; ++q) F[0][IN][c * N + q] = e[q];
+            }
+            // mask bytes are 0/1: one multiply packs the four of them into a nibble, cell v -> bit 3-v
+            unsigned mb = (*reinterpret_cast<const unsigned *>(sl + ROW_BYTES + lane * 4) * 0x08040201u) >> 24;
+            if (edge) {
+                // ghost columns take the value and mask of their mirror cell, which sits in this
+                // strip's ring slot (copied by another lane).  Lanes that lie wholly outside the
+                // allocation copied nothing: their slot bytes are stale, so clamp the nibble first.
+                mb &= 15u;
 #pragma unroll
-                            for (int v = 0; v < V; ++v) { FA[s][v] = FB[s][v]; FB[s][v] = cur[v]; }
-                            FBL[s] = shfl_up1(cur[V - 1]);
-                            FBR[s] = shfl_down1(cur[0]);
-                        } else {
-                            // CCST macro-stage: cur is row yy = y-2s of sweep s
-                            //   hC = L f (row yy-1), b = L h (row yy-2), out = sweep s+1 of row yy-2
-                            const unsigned kb = (unsigned)(mhist >> ((2 * s + 2) * V)) & VM;
-                            T hC[V], bh[V];
-                            lap_row<T, V>(FA[s], FB[s], cur, FBL[s], FBR[s], hC);
-                            lap_row<T, V>(HA[s], HB[s], hC, HBL[s], HBR[s], bh);
-#pragma unroll
-                            for (int v = 0; v < V; ++v) {
-                                const T c = FA[s][v];
-                                const T step = a.tension * HB[s][v] - a.one_minus_tension * bh[v];
-                                const T cand = c + dt * step;
-                                out[v] = ((kb >> v) & 1u) ? c : cand;
-                            }
-                            if (s == K - 1 && a.do_norm) {
-                                const int yo = y - H;
-                                if (out_lane && yo >= y0 && yo < y1 && yo >= 0 && yo < a.rows) {
-#pragma unroll
-                                    for (int v = 0; v < V; ++v) {
-                                        if (col0 + v < a.cols) {
-                                            const T d = out[v] - FA[s][v];
-                                            const double dd = (double)d;
-                                            n_d2 += dd * dd;
-                                            n_f2 += (double)out[v] * (double)out[v];
-                                            const double ad = fabs(dd);
-                                            if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
-                                        }
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int v = 0; v < V; ++v) {
-                                FA[s][v] = FB[s][v]; FB[s][v] = cur[v];
-                                HA[s][v] = HB[s][v]; HB[s][v] = hC[v];
-                            }
-                            FBL[s] = shfl_up1(cur[V - 1]);
-                            FBR[s] = shfl_down1(cur[0]);
-                            HBL[s] = shfl_up1(hC[V - 1]);
-                            HBR[s] = shfl_down1(hC[0]);
-                        }
-#pragma unroll
-                        for (int v = 0; v < V; ++v) cur[v] = out[v];
+                for (int q = 0; q < V; ++q) {
+                    const int c = col0 + q;
+                    if (c < 0 || c >= a.cols) {
+                        int cm = (c < 0) ? -c : 2 * (a.cols - 1) - c;
+                        int pos = max(0, min(32 * V - 1, cm - x0));
+                        const int pl = pos / V, pq = pos % V;
+                        F[0][IN][q] = *reinterpret_cast<const T *>(sl + (pq / N) * 512 + pl * 16 + (pq % N) * (int)sizeof(T));
+                        const unsigned kb = sl[ROW_BYTES + pos] ? 1u : 0u;
+                        mb = (mb & ~(8u >> q)) | (kb << (3 - q));
                     }
-                    // cur is now sweep K of row y-H
-                    const int yo = y - H;
-                    if (out_lane && yo >= y0 && yo < y1)
-                        store_row_vec<T, V>(a.dst + (long long)yo * a.pitch + col0, cur);
                 }
             }
+            mhist = (mhist << 4) | (unsigned long long)mb;
+            {   // refill the slot read one step ago with row y + D - 1
+                int ns = slot - 1;
+                if (ns < 0) ns += D;
+                issue(y + D - 1, ns);
+            }
+            slot = (slot + 1 == D) ? 0 : slot + 1;
+
+            T res[V];
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const T(&rin)[V] = F[s][IN];        // newest row of this stage's input field
+                const T nl = shfl_up1(rin[V - 1]), nr = shfl_down1(rin[0]);   // its halos, for next step
+                T o[V];
+                if (!CC) {
+                    // centre row F[s][IC] (row y-s-1), above F[s][IU], below rin
+                    const unsigned kb = (unsigned)(mhist >> ((s + 1) * 4)) & 15u;
+                    T s4[V];
+                    sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const T c = F[s][IC][v];
+                        const T cand = c + dt * (s4[v] - T(4) * c);
+                        o[v] = ((kb >> (3 - v)) & 1u) ? c : cand;
+                    }
+                } else {
+                    // rin is row yy = y-2s of sweep s; hN = L f (row yy-1); output = sweep s+1 of row yy-2
+                    const unsigned kb = (unsigned)(mhist >> ((2 * s + 2) * 4)) & 15u;
+                    T s4[V];
+                    sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) Hh[s][IN][v] = s4[v] - T(4) * F[s][IC][v];
+                    const T hl = shfl_up1(Hh[s][IN][V - 1]), hr = shfl_down1(Hh[s][IN][0]);
+                    sum4_row<T, V>(Hh[s][IU], Hh[s][IC], Hh[s][IN], HL[s], HR[s], s4);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const T c = F[s][IU][v];
+                        const T cand = (c + c2 * s4[v]) + c3 * Hh[s][IC][v];
+                        o[v] = ((kb >> (3 - v)) & 1u) ? c : cand;
+                    }
+                    HL[s] = hl; HR[s] = hr;
+                }
+                if (s == K - 1 && a.do_norm) {
+                    const int yo = y - H;
+                    if (out_lane && yo >= y0 && yo < y1 && yo >= 0 && yo < a.rows) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            if (col0 + v < a.cols) {
+                                const T prev = CC ? F[s][IU][v] : F[s][IC][v];
+                                const double dd = (double)(T)(o[v] - prev);
+                                n_d2 += dd * dd;
+                                n_f2 += (double)o[v] * (double)o[v];
+                                const double ad = fabs(dd);
+                                if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
+                            }
+                        }
+                    }
+                }
+                FL[s] = nl; FR[s] = nr;
+                if (s < K - 1) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) F[s + 1][IN][v] = o[v];
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) res[v] = o[v];
+                }
+            }
+            // res is sweep K of row y-H
+            const int yo = y - H;
+            if (out_lane && yo >= y0 && yo < y1)
+                store_row_vec<T, V>(a.dst + (long long)yo * a.pitch + col0, res);
+        };
+
+        for (int y = ybeg; y < yend; y += 3) {
+            step(Phase<0>(), y);
+            if (y + 1 < yend) step(Phase<1>(), y + 1);
+            if (y + 2 < yend) step(Phase<2>(), y + 2);
         }
+        cp_async_wait<0>();
     }
     if (a.do_norm) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -279,7 +295,9 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
 {
     constexpr int R = (METHOD == HMI_CCST) ? 2 : 1;
     constexpr int H = K * R, HV = ((H + V - 1) / V) * V, S = 32 * V - 2 * HV;
-    constexpr int PF = 4, WPB = 4, MINB = 2;
+    constexpr int D = 8, WPB = 4, MINB = 2;
+    constexpr int SLOT = 32 * V * (int)sizeof(T) + 32 * V;
+    constexpr size_t SMEM = (size_t)WPB * D * SLOT;
     StreamArgs<T> a = a0;
     a.nwin = (a.cols + S - 1) / S;
     const int nrows = a.row_hi - a.row_lo;
@@ -288,7 +306,14 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
     const long long warps = (long long)a.nwin * a.nchunks;
     const int blocks = (int)((warps + WPB - 1) / WPB);
     if (nblocks_out) *nblocks_out = blocks;
-    stream_kernel<T, V, K, METHOD, PF, WPB, MINB><<<blocks, WPB * 32, 0, st>>>(a);
+    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB>;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<blocks, WPB * 32, SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
