@@ -66,6 +66,7 @@ struct hmi_solver {
     bool use_stream = false;
     int tb = 1;              // sweeps fused per launch
     int chunk_rows = 0;      // 0 = auto
+    int vec = 0;             // streaming kernel: cells per lane (0 = default)
     long long launches = 0;
     bool has_problem = false;
 };
@@ -91,6 +92,7 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
         a.read_lo = -p.ghost_top; a.read_hi = p.rows + p.ghost_bottom;
         a.top_border = p.ghost_top == 0; a.bottom_border = p.ghost_bottom == 0;
         a.chunk_rows = s->chunk_rows;
+        a.vec = s->vec;
         a.dt = (T)p.dt; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
         a.do_norm = do_norm ? 1 : 0;
         a.partials = s->d_partials; a.counter = s->d_counter; a.result = s->d_result;
@@ -326,6 +328,11 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
     if (!strcmp(key, "chunk_rows")) {
         if (value < 0) return fail(HMI_ERR_BAD_ARG, "chunk_rows must be >= 0");
         s->chunk_rows = value == 0 ? 0 : (value < 8 ? 8 : (int)value);
+        return HMI_OK;
+    }
+    if (!strcmp(key, "vec")) {
+        if (value != 0 && value != 2 && value != 4) return fail(HMI_ERR_BAD_ARG, "vec must be 0, 2 or 4");
+        s->vec = (int)value;
         return HMI_OK;
     }
     if (!strcmp(key, "temporal_block")) {

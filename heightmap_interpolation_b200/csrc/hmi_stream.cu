@@ -7,11 +7,11 @@
 //     V consecutive cells of the current row in registers; x-neighbours come from warp shuffles,
 //     y-neighbours from the previous rows kept in registers.  No block barrier on the hot loop.
 //   * Rows are staged through a per-warp shared-memory ring filled by asynchronous 16-byte copies
-//     (cp.async / LDGSTS, coalesced: a warp moves one 1 KiB fp64 row segment per copy pair) issued
-//     D-1 rows ahead, so ~D KiB per warp are in flight without holding registers or coupling to
-//     the load scoreboard.  Each lane reads back only what it copied itself, so the ring needs no
-//     barrier either (edge strips, which mirror ghost columns out of other lanes' data, use a
-//     __syncwarp).
+//     (cp.async / LDGSTS; with V*sizeof(T) == 16 every copy instruction moves one fully coalesced
+//     512-byte row segment) issued D-1 rows ahead, so several KiB per warp are in flight without
+//     holding registers or coupling to the load scoreboard.
+//   * Two code paths per instantiation: interior strips run a lean loop; strips that touch a grid
+//     edge (mirrored ghost columns / rows) run the general one.
 //   * Temporal blocking: K relaxation sweeps are fused as a K-stage software pipeline in
 //     registers.  Row y enters stage 0 as it is loaded; stage s emits sweep s+1 of row y-r(s+1)
 //     (r = stencil radius: 1 harmonic, 2 CCST).  Only the K-th iterate is written back, so HBM
@@ -32,21 +32,6 @@ namespace hmi {
 template <typename T> struct Chunk16;
 template <> struct Chunk16<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct Chunk16<double> { typedef double2 type; static constexpr int N = 2; };
-
-template <typename T, int V>
-__device__ __forceinline__ void store_row_vec(T *__restrict__ p, const T (&v)[V])
-{
-    typedef typename Chunk16<T>::type C;
-    constexpr int N = Chunk16<T>::N;
-#pragma unroll
-    for (int c = 0; c < V / N; ++c) {
-        C t;
-        T *e = reinterpret_cast<T *>(&t);
-#pragma unroll
-        for (int q = 0; q < N; ++q) e[q] = v[c * N + q];
-        reinterpret_cast<C *>(p)[c] = t;
-    }
-}
 
 __device__ __forceinline__ unsigned smem_u32(const void *p)
 {
@@ -71,6 +56,23 @@ __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xfffffff
 
 template <int PH> struct Phase { static constexpr int value = PH; };
 
+// Geometry of one instantiation
+template <typename T, int V, int K, int METHOD>
+struct Geo {
+    static constexpr int N = Chunk16<T>::N;             // cells per 16-byte chunk
+    static constexpr int NCH = V / N;                   // 16-byte chunks per lane per row
+    static constexpr int R = (METHOD == HMI_CCST) ? 2 : 1;
+    static constexpr int H = K * R;                     // rows/columns of halo one launch consumes
+    static constexpr int HV = ((H + V - 1) / V) * V;    // column halo rounded to whole lanes
+    static constexpr int S = 32 * V - 2 * HV;           // columns a warp produces
+    static constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
+    static constexpr int MW = 8 * V + (V < 4 ? 1 : 0);  // 4-byte mask words copied per row
+    static constexpr int MB = ((4 * MW + 15) / 16) * 16;
+    static constexpr int SLOT = ROW_BYTES + MB;         // one row segment + its mask bytes
+    static_assert(V % N == 0 && NCH >= 1, "a lane moves whole 16-byte chunks");
+    static_assert(S > 0, "temporal block too deep for this strip width");
+};
+
 // Sum of the four neighbours of centre row b (rows above/below + lane halos)
 template <typename T, int V>
 __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], const T (&dn)[V], T bl, T br,
@@ -84,205 +86,244 @@ __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], cons
     }
 }
 
+// One warp streams its strip down one chunk of rows.  EDGE = the strip touches a grid edge (ghost
+// columns to mirror, rows to reflect or clamp); interior strips skip all of that.
+template <typename T, int V, int K, int METHOD, int D, bool EDGE>
+__device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned char *ring, const int lane,
+                                            const int win, const int chunk, double &n_d2, double &n_f2,
+                                            double &n_mx, double &n_nan)
+{
+    typedef Geo<T, V, K, METHOD> G;
+    typedef typename Chunk16<T>::type C16;
+    constexpr int N = G::N, NCH = G::NCH, R = G::R, H = G::H, HV = G::HV, S = G::S;
+    constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT, MW = G::MW;
+    constexpr bool CC = (METHOD == HMI_CCST);
+    constexpr unsigned VMASK = (1u << V) - 1u;
+    constexpr int LAG = H;                         // step y emits sweep K of row y - LAG
+    static_assert((R * (K - 1) + R + 1) * V <= 64, "mask history does not fit 64 bits");
+
+    const int x0 = win * S - HV;
+    const int col0 = x0 + lane * V;
+    const int y0 = a.row_lo + chunk * a.chunk_rows;
+    const int y1 = min(a.row_hi, y0 + a.chunk_rows);
+    const int ybeg = y0 - H, yend = y1 + H;        // rows streamed: [ybeg, yend)
+    const bool out_lane = (lane >= HV / V) && (lane < 32 - HV / V) && (col0 < a.cols);
+    const T dt = a.dt;
+    // CCST with folded coefficients: f' = f + c2*(sum of h's four neighbours) + c3*h,
+    //   c2 = -dt(1-t), c3 = dt*t - 4*c2      (== f + dt*(t*h - (1-t)*L h))
+    const T c2 = -(dt * a.one_minus_tension);
+    const T c3 = dt * a.tension - T(4) * c2;
+
+    // mask bytes of the strip start at column x0; the copy starts at the 4-byte boundary below it
+    const int moff = x0 & 3;
+    const int mx0 = x0 - moff;
+    const bool f_copies = EDGE ? ((col0 >= 0) && (col0 + V <= (int)a.pitch)) : true;
+    const bool m_copies = (lane < MW) &&
+                          (EDGE ? ((mx0 + 4 * lane >= 0) && (mx0 + 4 * lane + 4 <= (int)a.mpitch)) : true);
+
+    // Pipeline state.  Stage s keeps a 3-row window of its input field in F[s][0..2]; the row loop
+    // is unrolled by 3 so the window rotates by renaming (no register moves): in phase PH the rows
+    // above / centre / new sit in slots PH, PH+1, PH+2 (mod 3).  Stage s writes its output row
+    // straight into the new-row slot of stage s+1.
+    T F[K][3][V];
+    T Hh[CC ? K : 1][3][V];                        // CCST: window of h = L f
+    T FL[K], FR[K], HL[CC ? K : 1], HR[CC ? K : 1];
+    unsigned long long mhist = 0ull;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        FL[s] = FR[s] = T(0);
+        if (CC) HL[s] = HR[s] = T(0);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                F[s][q][v] = T(0);
+                if (CC) Hh[s][q][v] = T(0);
+            }
+    }
+
+    const T *gbase = a.src + col0;
+    const uint8_t *mbase = a.mask + mx0 + 4 * lane;
+    const unsigned ring_f = smem_u32(ring) + lane * 16;
+    const unsigned ring_m = smem_u32(ring) + ROW_BYTES + lane * 4;
+
+    // asynchronous copy of row y into ring slot `slot`
+    auto issue = [&](int y, int slot) {
+        if (y < yend) {
+            int ry = y;
+            if (EDGE) {                            // reflect-101 at global edges, clamp to memory
+                if (ry < 0 && a.top_border) ry = -ry;
+                else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
+                ry = max(a.read_lo, min(a.read_hi - 1, ry));
+            }
+            if (f_copies) {
+                const T *prow = gbase + (long long)ry * a.pitch;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + slot * SLOT + c * 512, prow + c * N);
+            }
+            if (m_copies) cp_async4(ring_m + slot * SLOT, mbase + (long long)ry * a.mpitch);
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int u = 0; u < D - 1; ++u) issue(ybeg + u, u);
+
+    int slot = 0;
+    T *dptr = a.dst + (long long)(ybeg - LAG) * a.pitch + col0;   // row emitted by step ybeg
+
+    auto step = [&](auto ph, const int y) {
+        constexpr int PH = decltype(ph)::value;
+        constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
+        cp_async_wait<D - 2>();                    // this lane's copies of row y have landed
+        if (EDGE || V < 4) __syncwarp();           // ... and the other lanes' (mask words, mirrors)
+        const unsigned char *sl = ring + slot * SLOT;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const C16 t = *reinterpret_cast<const C16 *>(sl + c * 512 + lane * 16);
+            const T *e = reinterpret_cast<const T *>(&t);
+#pragma unroll
+            for (int q = 0; q < N; ++q) F[0][IN][c * N + q] = e[q];
+        }
+        // mask bytes are 0/1: one multiply packs them into V bits, cell v -> bit V-1-v
+        unsigned mb;
+        if (V == 4)
+            mb = (*reinterpret_cast<const unsigned *>(sl + ROW_BYTES + moff + lane * 4) * 0x08040201u) >> 24;
+        else
+            mb = ((unsigned)*reinterpret_cast<const unsigned short *>(sl + ROW_BYTES + moff + lane * 2) * 0x0201u) >> 8;
+        if (EDGE) {
+            // Ghost columns take the value and mask of their mirror cell, which sits in this
+            // strip's ring slot (copied by another lane).  Lanes outside the allocation copied
+            // nothing and read stale bytes, so clamp the bit group first.
+            mb &= VMASK;
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const int c = col0 + q;
+                if (c < 0 || c >= a.cols) {
+                    const int cm = (c < 0) ? -c : 2 * (a.cols - 1) - c;
+                    const int pos = max(0, min(32 * V - 1, cm - x0));
+                    const int pl = pos / V, pq = pos % V;
+                    F[0][IN][q] = *reinterpret_cast<const T *>(sl + (pq / N) * 512 + pl * 16 + (pq % N) * (int)sizeof(T));
+                    const unsigned kb = sl[ROW_BYTES + moff + pos] ? 1u : 0u;
+                    mb = (mb & ~(1u << (V - 1 - q))) | (kb << (V - 1 - q));
+                }
+            }
+        } else if (V < 4) {
+            mb &= VMASK;
+        }
+        mhist = (mhist << V) | (unsigned long long)mb;
+        {   // refill the slot read one step ago with row y + D - 1
+            int ns = slot - 1;
+            if (ns < 0) ns += D;
+            issue(y + D - 1, ns);
+        }
+        slot = (slot + 1 == D) ? 0 : slot + 1;
+
+        T res[V];
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            const T(&rin)[V] = F[s][IN];           // newest row of this stage's input field
+            const T nl = shfl_up1(rin[V - 1]), nr = shfl_down1(rin[0]);   // its halos, for next step
+            T o[V];
+            const unsigned kb = (unsigned)(mhist >> ((R * s + R) * V)) & VMASK;
+            T s4[V];
+            sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
+            if (!CC) {
+                // centre row F[s][IC] (row y-s-1), above F[s][IU], below rin
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const T c = F[s][IC][v];
+                    const T cand = c + dt * (s4[v] - T(4) * c);
+                    o[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
+                }
+            } else {
+                // rin is row yy = y-2s of sweep s; hN = L f (row yy-1); output = sweep s+1 of row yy-2
+#pragma unroll
+                for (int v = 0; v < V; ++v) Hh[s][IN][v] = s4[v] - T(4) * F[s][IC][v];
+                const T hl = shfl_up1(Hh[s][IN][V - 1]), hr = shfl_down1(Hh[s][IN][0]);
+                sum4_row<T, V>(Hh[s][IU], Hh[s][IC], Hh[s][IN], HL[s], HR[s], s4);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const T c = F[s][IU][v];
+                    const T cand = (c + c2 * s4[v]) + c3 * Hh[s][IC][v];
+                    o[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
+                }
+                HL[s] = hl; HR[s] = hr;
+            }
+            if (s == K - 1 && a.do_norm) {
+                const int yo = y - LAG;
+                if (out_lane && yo >= y0 && yo < y1 && yo >= 0 && yo < a.rows) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if (col0 + v < a.cols) {
+                            const T prev = CC ? F[s][IU][v] : F[s][IC][v];
+                            const double dd = (double)(T)(o[v] - prev);
+                            n_d2 += dd * dd;
+                            n_f2 += (double)o[v] * (double)o[v];
+                            const double ad = fabs(dd);
+                            if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
+                        }
+                    }
+                }
+            }
+            FL[s] = nl; FR[s] = nr;
+            if (s < K - 1) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) F[s + 1][IN][v] = o[v];
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) res[v] = o[v];
+            }
+        }
+        // res is sweep K of row y-LAG
+        const int yo = y - LAG;
+        if (out_lane && yo >= y0 && yo < y1) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                C16 t;
+                T *e = reinterpret_cast<T *>(&t);
+#pragma unroll
+                for (int q = 0; q < N; ++q) e[q] = res[c * N + q];
+                reinterpret_cast<C16 *>(dptr)[c] = t;
+            }
+        }
+        dptr += a.pitch;
+    };
+
+    for (int y = ybeg; y < yend; y += 3) {
+        step(Phase<0>(), y);
+        if (y + 1 < yend) step(Phase<1>(), y + 1);
+        if (y + 2 < yend) step(Phase<2>(), y + 2);
+    }
+    cp_async_wait<0>();
+}
+
 template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB>
 __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs<T> a)
 {
-    static_assert(V == 4, "the shared-memory ring moves 4 mask bytes per lane");
-    typedef typename Chunk16<T>::type C16;
-    constexpr int N = Chunk16<T>::N;               // cells per 16-byte chunk
-    constexpr int NCH = V / N;                     // 16-byte chunks per lane per row
-    constexpr int R = (METHOD == HMI_CCST) ? 2 : 1;
-    constexpr int H = K * R;                       // rows/columns of halo one launch consumes
-    constexpr int HV = ((H + V - 1) / V) * V;      // column halo rounded to whole lanes
-    constexpr int S = 32 * V - 2 * HV;             // columns a warp produces
-    constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
-    constexpr int SLOT = ROW_BYTES + 32 * V;       // one row segment + its mask bytes
-    constexpr bool CC = (METHOD == HMI_CCST);
-    static_assert(S > 0, "temporal block too deep for this strip width");
-    static_assert(D >= 3, "ring too shallow");
-
+    typedef Geo<T, V, K, METHOD> G;
     extern __shared__ __align__(16) unsigned char ring_all[];
     __shared__ double sh[128];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    unsigned char *ring = ring_all + (size_t)wib * D * SLOT;
+    unsigned char *ring = ring_all + (size_t)wib * D * G::SLOT;
     const long long gw = (long long)blockIdx.x * WPB + wib;
     const int win = (int)(gw % a.nwin);
     const int chunk = (int)(gw / a.nwin);
     double n_d2 = 0.0, n_f2 = 0.0, n_mx = 0.0, n_nan = 0.0;
 
     if (chunk < a.nchunks) {
-        const int x0 = win * S - HV;
-        const int col0 = x0 + lane * V;
-        const bool edge = (x0 < 0) || (x0 + 32 * V > a.cols);
-        const bool copies = (col0 >= 0) && (col0 + V <= (int)a.pitch);   // lane's cells exist in memory
+        const int x0 = win * G::S - G::HV;
         const int y0 = a.row_lo + chunk * a.chunk_rows;
         const int y1 = min(a.row_hi, y0 + a.chunk_rows);
-        const bool out_lane = (lane >= HV / V) && (lane < 32 - HV / V) && (col0 < a.cols);
-        const T dt = a.dt;
-        // CCST with folded coefficients: f' = f + c2*(sum of h's four neighbours) + c3*h,
-        //   c2 = -dt(1-t), c3 = dt*t - 4*c2      (== f + dt*(t*h - (1-t)*L h))
-        const T c2 = -(dt * a.one_minus_tension);
-        const T c3 = dt * a.tension - T(4) * c2;
-
-        // Pipeline state.  Stage s keeps a 3-row window of its input field in F[s][0..2]; the row
-        // loop is unrolled by 3 so the window rotates by renaming (no register moves): in phase PH
-        // the rows above / centre / new sit in slots PH, PH+1, PH+2 (mod 3).  Stage s writes its
-        // output row straight into the new-row slot of stage s+1.
-        T F[K + 1][3][V];
-        T Hh[CC ? K : 1][3][V];                    // CCST: window of h = L f
-        T FL[K], FR[K], HL[CC ? K : 1], HR[CC ? K : 1];
-        unsigned long long mhist = 0ull;
-#pragma unroll
-        for (int s = 0; s < K; ++s) {
-            FL[s] = FR[s] = T(0);
-            if (CC) HL[s] = HR[s] = T(0);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    F[s][q][v] = T(0);
-                    if (CC) Hh[s][q][v] = T(0);
-                }
-        }
-
-        const int ybeg = y0 - H, yend = y1 + H;    // rows streamed: [ybeg, yend)
-        const T *gbase = a.src + col0;
-        const uint8_t *mbase = a.mask + col0;
-        const unsigned ring_f = smem_u32(ring) + lane * 16;
-        const unsigned ring_m = smem_u32(ring) + ROW_BYTES + lane * 4;
-
-        // asynchronous copy of row y (reflect-101 at global edges) into ring slot `slot`
-        auto issue = [&](int y, int slot) {
-            if (y < yend && copies) {
-                int ry = y;
-                if (ry < 0 && a.top_border) ry = -ry;
-                else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
-                ry = max(a.read_lo, min(a.read_hi - 1, ry));
-                const T *prow = gbase + (long long)ry * a.pitch;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + slot * SLOT + c * 512, prow + c * N);
-                cp_async4(ring_m + slot * SLOT, mbase + (long long)ry * a.mpitch);
-            }
-            cp_async_commit();
-        };
-
-#pragma unroll
-        for (int u = 0; u < D - 1; ++u) issue(ybeg + u, u);
-
-        int slot = 0;
-        auto step = [&](auto ph, const int y) {
-            constexpr int PH = decltype(ph)::value;
-            constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
-            cp_async_wait<D - 2>();                 // row y has landed (this lane's part)
-            if (edge) __syncwarp();                 // ... and every other lane's part
-            const unsigned char *sl = ring + slot * SLOT;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const C16 t = *reinterpret_cast<const C16 *>(sl + c * 512 + lane * 16);
-                const T *e = reinterpret_cast<const T *>(&t);
-#pragma unroll
-                for (int q = 0; q < N; ++q) F[0][IN][c * N + q] = e[q];
-            }
-            // mask bytes are 0/1: one multiply packs the four of them into a nibble, cell v -> bit 3-v
-            unsigned mb = (*reinterpret_cast<const unsigned *>(sl + ROW_BYTES + lane * 4) * 0x08040201u) >> 24;
-            if (edge) {
-                // ghost columns take the value and mask of their mirror cell, which sits in this
-                // strip's ring slot (copied by another lane).  Lanes that lie wholly outside the
-                // allocation copied nothing: their slot bytes are stale, so clamp the nibble first.
-                mb &= 15u;
-#pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    const int c = col0 + q;
-                    if (c < 0 || c >= a.cols) {
-                        int cm = (c < 0) ? -c : 2 * (a.cols - 1) - c;
-                        int pos = max(0, min(32 * V - 1, cm - x0));
-                        const int pl = pos / V, pq = pos % V;
-                        F[0][IN][q] = *reinterpret_cast<const T *>(sl + (pq / N) * 512 + pl * 16 + (pq % N) * (int)sizeof(T));
-                        const unsigned kb = sl[ROW_BYTES + pos] ? 1u : 0u;
-                        mb = (mb & ~(8u >> q)) | (kb << (3 - q));
-                    }
-                }
-            }
-            mhist = (mhist << 4) | (unsigned long long)mb;
-            {   // refill the slot read one step ago with row y + D - 1
-                int ns = slot - 1;
-                if (ns < 0) ns += D;
-                issue(y + D - 1, ns);
-            }
-            slot = (slot + 1 == D) ? 0 : slot + 1;
-
-            T res[V];
-#pragma unroll
-            for (int s = 0; s < K; ++s) {
-                const T(&rin)[V] = F[s][IN];        // newest row of this stage's input field
-                const T nl = shfl_up1(rin[V - 1]), nr = shfl_down1(rin[0]);   // its halos, for next step
-                T o[V];
-                if (!CC) {
-                    // centre row F[s][IC] (row y-s-1), above F[s][IU], below rin
-                    const unsigned kb = (unsigned)(mhist >> ((s + 1) * 4)) & 15u;
-                    T s4[V];
-                    sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const T c = F[s][IC][v];
-                        const T cand = c + dt * (s4[v] - T(4) * c);
-                        o[v] = ((kb >> (3 - v)) & 1u) ? c : cand;
-                    }
-                } else {
-                    // rin is row yy = y-2s of sweep s; hN = L f (row yy-1); output = sweep s+1 of row yy-2
-                    const unsigned kb = (unsigned)(mhist >> ((2 * s + 2) * 4)) & 15u;
-                    T s4[V];
-                    sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) Hh[s][IN][v] = s4[v] - T(4) * F[s][IC][v];
-                    const T hl = shfl_up1(Hh[s][IN][V - 1]), hr = shfl_down1(Hh[s][IN][0]);
-                    sum4_row<T, V>(Hh[s][IU], Hh[s][IC], Hh[s][IN], HL[s], HR[s], s4);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const T c = F[s][IU][v];
-                        const T cand = (c + c2 * s4[v]) + c3 * Hh[s][IC][v];
-                        o[v] = ((kb >> (3 - v)) & 1u) ? c : cand;
-                    }
-                    HL[s] = hl; HR[s] = hr;
-                }
-                if (s == K - 1 && a.do_norm) {
-                    const int yo = y - H;
-                    if (out_lane && yo >= y0 && yo < y1 && yo >= 0 && yo < a.rows) {
-#pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            if (col0 + v < a.cols) {
-                                const T prev = CC ? F[s][IU][v] : F[s][IC][v];
-                                const double dd = (double)(T)(o[v] - prev);
-                                n_d2 += dd * dd;
-                                n_f2 += (double)o[v] * (double)o[v];
-                                const double ad = fabs(dd);
-                                if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
-                            }
-                        }
-                    }
-                }
-                FL[s] = nl; FR[s] = nr;
-                if (s < K - 1) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) F[s + 1][IN][v] = o[v];
-                } else {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) res[v] = o[v];
-                }
-            }
-            // res is sweep K of row y-H
-            const int yo = y - H;
-            if (out_lane && yo >= y0 && yo < y1)
-                store_row_vec<T, V>(a.dst + (long long)yo * a.pitch + col0, res);
-        };
-
-        for (int y = ybeg; y < yend; y += 3) {
-            step(Phase<0>(), y);
-            if (y + 1 < yend) step(Phase<1>(), y + 1);
-            if (y + 2 < yend) step(Phase<2>(), y + 2);
-        }
-        cp_async_wait<0>();
+        const int ybeg = y0 - G::H, yend = y1 + G::H;
+        const bool col_edge = (x0 < 0) || (x0 + 32 * V > a.cols);
+        const bool row_edge = (ybeg < 0 && a.top_border) || (yend > a.rows && a.bottom_border) ||
+                              (ybeg < a.read_lo) || (yend > a.read_hi);
+        if (col_edge || row_edge)
+            stream_rows<T, V, K, METHOD, D, true>(a, ring, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+        else
+            stream_rows<T, V, K, METHOD, D, false>(a, ring, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
     }
     if (a.do_norm) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -293,15 +334,13 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
 template <typename T, int V, int K, int METHOD>
 static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nblocks_out)
 {
-    constexpr int R = (METHOD == HMI_CCST) ? 2 : 1;
-    constexpr int H = K * R, HV = ((H + V - 1) / V) * V, S = 32 * V - 2 * HV;
-    constexpr int D = 8, WPB = 4, MINB = 2;
-    constexpr int SLOT = 32 * V * (int)sizeof(T) + 32 * V;
-    constexpr size_t SMEM = (size_t)WPB * D * SLOT;
+    typedef Geo<T, V, K, METHOD> G;
+    constexpr int D = 8, WPB = 4, MINB = 1;
+    constexpr size_t SMEM = (size_t)WPB * D * G::SLOT;
     StreamArgs<T> a = a0;
-    a.nwin = (a.cols + S - 1) / S;
+    a.nwin = (a.cols + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
-    if (a.chunk_rows <= 0) a.chunk_rows = stream_auto_chunk_rows(nrows, a.nwin, H);
+    if (a.chunk_rows <= 0) a.chunk_rows = stream_auto_chunk_rows(nrows, a.nwin, G::H);
     a.nchunks = (nrows + a.chunk_rows - 1) / a.chunk_rows;
     const long long warps = (long long)a.nwin * a.nchunks;
     const int blocks = (int)((warps + WPB - 1) / WPB);
@@ -319,9 +358,9 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
 
 int stream_auto_chunk_rows(int nrows, int nwin, int halo)
 {
-    // enough warps for ~2 waves of 12 warps on each of the 148 SMs, but chunks tall enough that the
+    // enough warps for ~2 waves of 16 warps on each of the 148 SMs, but chunks tall enough that the
     // 2*halo redundant rows stay a small fraction
-    const long long target_warps = 148LL * 12 * 2;
+    const long long target_warps = 148LL * 16 * 2;
     long long chunks = (target_warps + nwin - 1) / nwin;
     if (chunks < 1) chunks = 1;
     long long ch = (nrows + chunks - 1) / chunks;
@@ -342,18 +381,17 @@ int stream_max_k(int method, int dtype)
 
 int stream_max_blocks(int method, int rows_total, int cols)
 {
-    // upper bound over every (K, chunk_rows >= 1) this file can launch: strips are >= 32 columns
-    // wide after the overlap, chunks at least 1 row; callers clamp chunk_rows >= 8
+    // upper bound over every (V, K, chunk_rows) this file can launch: strips produce >= 32 columns,
+    // chunks are >= 8 rows (callers clamp chunk_rows >= 8)
     const long long nwin = (cols + 31) / 32 + 1;
     const long long nch = (rows_total + 7) / 8 + 1;
     (void)method;
     return (int)((nwin * nch + 3) / 4 + 1);
 }
 
-template <typename T>
-cudaError_t launch_stream(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
+template <typename T, int V>
+static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
 {
-    constexpr int V = 4;
 #define HMI_CASE(M, KK) \
     if (method == M && k == KK) return launch_one<T, V, KK, M>(a, st, nblocks_out);
     HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 2) HMI_CASE(HMI_HARMONIC, 3)
@@ -364,7 +402,17 @@ cudaError_t launch_stream(int method, int k, const StreamArgs<T> &a, cudaStream_
     return cudaErrorInvalidValue;
 }
 
-template cudaError_t launch_stream<float>(int, int, const StreamArgs<float> &, cudaStream_t, int *);
-template cudaError_t launch_stream<double>(int, int, const StreamArgs<double> &, cudaStream_t, int *);
+template <>
+cudaError_t launch_stream<float>(int method, int k, const StreamArgs<float> &a, cudaStream_t st, int *nblocks_out)
+{
+    return launch_v<float, 4>(method, k, a, st, nblocks_out);
+}
+
+template <>
+cudaError_t launch_stream<double>(int method, int k, const StreamArgs<double> &a, cudaStream_t st, int *nblocks_out)
+{
+    if (a.vec == 4) return launch_v<double, 4>(method, k, a, st, nblocks_out);
+    return launch_v<double, 2>(method, k, a, st, nblocks_out);
+}
 
 }  // namespace hmi

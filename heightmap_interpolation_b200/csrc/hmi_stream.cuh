@@ -19,6 +19,7 @@ struct StreamArgs {
     int read_lo, read_hi;       // rows that exist in memory [read_lo, read_hi) (ghosts included)
     int top_border, bottom_border;
     int chunk_rows;             // rows per warp chunk; <= 0 = auto
+    int vec;                    // cells per lane (fp64: 2 or 4; 0 = default)
     int nwin, nchunks;          // filled by the launcher
     T dt, tension, one_minus_tension;
     int do_norm;

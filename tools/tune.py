@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--chunks", default="0,32,64,128,256")
     ap.add_argument("--sweeps", type=int, default=48)
     ap.add_argument("--mask", default="tracks")
+    ap.add_argument("--vecs", default="2,4")
     a = ap.parse_args()
     n = a.n
     for dt in a.dtypes.split(","):
@@ -60,19 +61,21 @@ def main():
                     if kernel == "stream" and method == "ccst" and tb > 4:
                         continue
                     chunks = [int(c) for c in a.chunks.split(",")] if kernel == "stream" else [0]
-                    for ch in chunks:
+                    for ch, sk in [(c, k) for c in chunks for k in ([int(x) for x in a.vecs.split(",")] if (kernel == "stream" and dt == "f64") else [0])]:
                         p = make_params(n, n, dtype, code, orientation=1, dt=step, tension=0.3, epsilon=1.0,
                                         kernel=C.KERNELS[kernel], temporal_block=tb)
                         with Solver(p) as s:
                             if ch:
                                 s.set_option("chunk_rows", ch)
+                            if kernel == "stream":
+                                s.set_option("vec", sk)
                             s.set_problem_host(img, mask)
                             nsw = a.sweeps if kernel == "stream" else max(4, a.sweeps // 4)
                             nsw = (nsw // tb) * tb
                             ms = time_sweeps(s, nsw)
                         g = n * n * nsw / (ms * 1e-3) / 1e9
-                        print("%-8s %s %-7s tb=%d chunk=%-4d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
-                              % (method, dt, kernel, tb, ch, g, 100 * g * bpl / 6550.4, g * bpl), flush=True)
+                        print("%-8s %s %-7s tb=%d chunk=%-4d vec=%d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
+                              % (method, dt, kernel, tb, ch, sk, g, 100 * g * bpl / 6550.4, g * bpl), flush=True)
 
 
 if __name__ == "__main__":
