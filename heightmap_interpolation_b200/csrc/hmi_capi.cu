@@ -152,6 +152,9 @@ int do_sweeps(hmi_solver *s, long long n, bool norm_on_last, cudaStream_t st)
     while (done < n) {
         long long k = n - done;
         if (k > s->tb) k = s->tb;
+        // the streaming kernel fuses the convergence sums into a single-sweep launch: keep the
+        // last sweep of a check window on its own
+        if (norm_on_last && s->use_stream && done + k == n && k > 1) k -= 1;
         const long long after = n - (done + k);  // sweeps still to run after this block
         const int lo = p.ghost_top > 0 ? (int)(-after * s->radius) : 0;
         const int hi = p.rows + (p.ghost_bottom > 0 ? (int)(after * s->radius) : 0);
@@ -274,7 +277,8 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     }
     if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
         const int maxk = hmi::stream_max_k(p.method, p.dtype);
-        tb = p.temporal_block > 0 ? p.temporal_block : (p.method == HMI_CCST ? 2 : 4);
+        tb = p.temporal_block > 0 ? p.temporal_block
+                                  : (p.method == HMI_CCST ? (p.dtype == HMI_F64 ? 3 : 4) : 6);
         if (tb > maxk) tb = maxk;
         // the mirrored ghost loads need the mirror cell to exist: shrink the block on small grids
         const int min_dim = p.cols < p.rows ? p.cols : p.rows;

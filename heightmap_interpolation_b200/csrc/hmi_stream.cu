@@ -56,6 +56,22 @@ __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xfffffff
 
 template <int PH> struct Phase { static constexpr int value = PH; };
 
+__device__ __forceinline__ void lds16(unsigned addr, double (&v)[2])
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+}
+__device__ __forceinline__ void lds16(unsigned addr, float (&v)[4])
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ unsigned lds32(unsigned addr)
+{
+    unsigned r;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(r) : "r"(addr));
+    return r;
+}
+
 // Geometry of one instantiation
 template <typename T, int V, int K, int METHOD>
 struct Geo {
@@ -66,10 +82,9 @@ struct Geo {
     static constexpr int HV = ((H + V - 1) / V) * V;    // column halo rounded to whole lanes
     static constexpr int S = 32 * V - 2 * HV;           // columns a warp produces
     static constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
-    static constexpr int MW = 8 * V + (V < 4 ? 1 : 0);  // 4-byte mask words copied per row
-    static constexpr int MB = ((4 * MW + 15) / 16) * 16;
-    static constexpr int SLOT = ROW_BYTES + MB;         // one row segment + its mask bytes
+    static constexpr int SLOT = ROW_BYTES + 128;        // one row segment + one mask word per lane
     static_assert(V % N == 0 && NCH >= 1, "a lane moves whole 16-byte chunks");
+    static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
     static_assert(S > 0, "temporal block too deep for this strip width");
 };
 
@@ -87,20 +102,22 @@ __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], cons
 }
 
 // One warp streams its strip down one chunk of rows.  EDGE = the strip touches a grid edge (ghost
-// columns to mirror, rows to reflect or clamp); interior strips skip all of that.
-template <typename T, int V, int K, int METHOD, int D, bool EDGE>
-__device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned char *ring, const int lane,
+// columns to mirror, rows to reflect or clamp); interior strips skip all of that and address
+// memory incrementally.  NORM = accumulate the convergence sums of the (single) sweep.
+template <typename T, int V, int K, int METHOD, int D, bool EDGE, bool NORM>
+__device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsigned ring_s, const int lane,
                                             const int win, const int chunk, double &n_d2, double &n_f2,
                                             double &n_mx, double &n_nan)
 {
     typedef Geo<T, V, K, METHOD> G;
     typedef typename Chunk16<T>::type C16;
     constexpr int N = G::N, NCH = G::NCH, R = G::R, H = G::H, HV = G::HV, S = G::S;
-    constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT, MW = G::MW;
+    constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT;
     constexpr bool CC = (METHOD == HMI_CCST);
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int LAG = H;                         // step y emits sweep K of row y - LAG
-    static_assert((R * (K - 1) + R + 1) * V <= 64, "mask history does not fit 64 bits");
+    static_assert((H + 1) * V <= 64, "mask history does not fit 64 bits");
+    static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
 
     const int x0 = win * S - HV;
     const int col0 = x0 + lane * V;
@@ -114,12 +131,13 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned cha
     const T c2 = -(dt * a.one_minus_tension);
     const T c3 = dt * a.tension - T(4) * c2;
 
-    // mask bytes of the strip start at column x0; the copy starts at the 4-byte boundary below it
-    const int moff = x0 & 3;
-    const int mx0 = x0 - moff;
+    // Each lane copies the aligned 4-byte mask word that holds its V mask bytes (V = 2: two lanes
+    // fetch the same word), so no lane ever reads ring bytes another lane wrote — except the edge
+    // path, which mirrors ghost columns out of other lanes' slots.
+    const int mcol = col0 & ~3;
+    const unsigned msh = (unsigned)(col0 & 3) * 8u;
     const bool f_copies = EDGE ? ((col0 >= 0) && (col0 + V <= (int)a.pitch)) : true;
-    const bool m_copies = (lane < MW) &&
-                          (EDGE ? ((mx0 + 4 * lane >= 0) && (mx0 + 4 * lane + 4 <= (int)a.mpitch)) : true);
+    const bool m_copies = EDGE ? ((mcol >= 0) && (mcol + 4 <= (int)a.mpitch)) : true;
 
     // Pipeline state.  Stage s keeps a 3-row window of its input field in F[s][0..2]; the row loop
     // is unrolled by 3 so the window rotates by renaming (no register moves): in phase PH the rows
@@ -142,55 +160,65 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned cha
             }
     }
 
+    const unsigned ring_f = ring_s + lane * 16;                // this lane's first 16-byte chunk
+    const unsigned ring_m = ring_s + ROW_BYTES + lane * 4;     // this lane's mask word
     const T *gbase = a.src + col0;
-    const uint8_t *mbase = a.mask + mx0 + 4 * lane;
-    const unsigned ring_f = smem_u32(ring) + lane * 16;
-    const unsigned ring_m = smem_u32(ring) + ROW_BYTES + lane * 4;
+    const uint8_t *mbase = a.mask + mcol;
+    // running state of the copy engine: next row to fetch and where
+    int ynext = ybeg;
+    unsigned wofs = 0;                                         // ring byte offset of the slot to fill
+    const T *gnext = gbase + (long long)ybeg * a.pitch;        // interior path: incremental
+    const uint8_t *mnext = mbase + (long long)ybeg * a.mpitch;
 
-    // asynchronous copy of row y into ring slot `slot`
-    auto issue = [&](int y, int slot) {
-        if (y < yend) {
-            int ry = y;
+    auto issue = [&]() {
+        if (ynext < yend) {
+            const T *prow = gnext;
+            const uint8_t *mrow = mnext;
             if (EDGE) {                            // reflect-101 at global edges, clamp to memory
+                int ry = ynext;
                 if (ry < 0 && a.top_border) ry = -ry;
                 else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
                 ry = max(a.read_lo, min(a.read_hi - 1, ry));
+                prow = gbase + (long long)ry * a.pitch;
+                mrow = mbase + (long long)ry * a.mpitch;
             }
             if (f_copies) {
-                const T *prow = gbase + (long long)ry * a.pitch;
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + slot * SLOT + c * 512, prow + c * N);
+                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + wofs + c * 512, prow + c * N);
             }
-            if (m_copies) cp_async4(ring_m + slot * SLOT, mbase + (long long)ry * a.mpitch);
+            if (m_copies) cp_async4(ring_m + wofs, mrow);
         }
         cp_async_commit();
+        ++ynext;
+        if (!EDGE) { gnext += a.pitch; mnext += a.mpitch; }
+        wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
     };
 
 #pragma unroll
-    for (int u = 0; u < D - 1; ++u) issue(ybeg + u, u);
+    for (int u = 0; u < D - 1; ++u) issue();
 
-    int slot = 0;
+    unsigned rofs = 0;                                         // ring byte offset of the slot to read
     T *dptr = a.dst + (long long)(ybeg - LAG) * a.pitch + col0;   // row emitted by step ybeg
 
     auto step = [&](auto ph, const int y) {
         constexpr int PH = decltype(ph)::value;
         constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
         cp_async_wait<D - 2>();                    // this lane's copies of row y have landed
-        if (EDGE || V < 4) __syncwarp();           // ... and the other lanes' (mask words, mirrors)
-        const unsigned char *sl = ring + slot * SLOT;
+        if (EDGE) __syncwarp();                    // ... and the other lanes' (for the mirrors)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            const C16 t = *reinterpret_cast<const C16 *>(sl + c * 512 + lane * 16);
-            const T *e = reinterpret_cast<const T *>(&t);
+            T e[N];
+            lds16(ring_f + rofs + c * 512, e);
 #pragma unroll
             for (int q = 0; q < N; ++q) F[0][IN][c * N + q] = e[q];
         }
         // mask bytes are 0/1: one multiply packs them into V bits, cell v -> bit V-1-v
         unsigned mb;
-        if (V == 4)
-            mb = (*reinterpret_cast<const unsigned *>(sl + ROW_BYTES + moff + lane * 4) * 0x08040201u) >> 24;
-        else
-            mb = ((unsigned)*reinterpret_cast<const unsigned short *>(sl + ROW_BYTES + moff + lane * 2) * 0x0201u) >> 8;
+        {
+            const unsigned w = lds32(ring_m + rofs);
+            if (V == 4) mb = (w * 0x08040201u) >> 24;
+            else mb = ((((w >> msh) & 0xffffu) * 0x0201u) >> 8) & 3u;
+        }
         if (EDGE) {
             // Ghost columns take the value and mask of their mirror cell, which sits in this
             // strip's ring slot (copied by another lane).  Lanes outside the allocation copied
@@ -203,21 +231,22 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned cha
                     const int cm = (c < 0) ? -c : 2 * (a.cols - 1) - c;
                     const int pos = max(0, min(32 * V - 1, cm - x0));
                     const int pl = pos / V, pq = pos % V;
-                    F[0][IN][q] = *reinterpret_cast<const T *>(sl + (pq / N) * 512 + pl * 16 + (pq % N) * (int)sizeof(T));
-                    const unsigned kb = sl[ROW_BYTES + moff + pos] ? 1u : 0u;
+                    T e[N];
+                    lds16(ring_s + rofs + (pq / N) * 512 + pl * 16, e);
+                    T val = e[0];
+#pragma unroll
+                    for (int j = 1; j < N; ++j) if ((pq % N) == j) val = e[j];
+                    F[0][IN][q] = val;
+                    const int pmcol = (x0 + pl * V) & ~3;
+                    const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
+                    const unsigned kb = (w >> (8 * (x0 + pos - pmcol))) & 1u;
                     mb = (mb & ~(1u << (V - 1 - q))) | (kb << (V - 1 - q));
                 }
             }
-        } else if (V < 4) {
-            mb &= VMASK;
         }
         mhist = (mhist << V) | (unsigned long long)mb;
-        {   // refill the slot read one step ago with row y + D - 1
-            int ns = slot - 1;
-            if (ns < 0) ns += D;
-            issue(y + D - 1, ns);
-        }
-        slot = (slot + 1 == D) ? 0 : slot + 1;
+        rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
+        issue();                                   // refills the slot read one step ago
 
         T res[V];
 #pragma unroll
@@ -250,7 +279,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned cha
                 }
                 HL[s] = hl; HR[s] = hr;
             }
-            if (s == K - 1 && a.do_norm) {
+            if (NORM) {
                 const int yo = y - LAG;
                 if (out_lane && yo >= y0 && yo < y1 && yo >= 0 && yo < a.rows) {
 #pragma unroll
@@ -298,15 +327,15 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, unsigned cha
     cp_async_wait<0>();
 }
 
-template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB>
+template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM>
 __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs<T> a)
 {
     typedef Geo<T, V, K, METHOD> G;
     extern __shared__ __align__(16) unsigned char ring_all[];
-    __shared__ double sh[128];
+    __shared__ double sh[NORM ? 128 : 1];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    unsigned char *ring = ring_all + (size_t)wib * D * G::SLOT;
+    const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * D * G::SLOT;
     const long long gw = (long long)blockIdx.x * WPB + wib;
     const int win = (int)(gw % a.nwin);
     const int chunk = (int)(gw / a.nwin);
@@ -321,17 +350,17 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
         const bool row_edge = (ybeg < 0 && a.top_border) || (yend > a.rows && a.bottom_border) ||
                               (ybeg < a.read_lo) || (yend > a.read_hi);
         if (col_edge || row_edge)
-            stream_rows<T, V, K, METHOD, D, true>(a, ring, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, true, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows<T, V, K, METHOD, D, false>(a, ring, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, false, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
     }
-    if (a.do_norm) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
+    if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 
-template <typename T, int V, int K, int METHOD>
+template <typename T, int V, int K, int METHOD, bool NORM>
 static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nblocks_out)
 {
     typedef Geo<T, V, K, METHOD> G;
@@ -345,7 +374,7 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
     const long long warps = (long long)a.nwin * a.nchunks;
     const int blocks = (int)((warps + WPB - 1) / WPB);
     if (nblocks_out) *nblocks_out = blocks;
-    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB>;
+    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -392,8 +421,14 @@ int stream_max_blocks(int method, int rows_total, int cols)
 template <typename T, int V>
 static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
 {
+    if (a.do_norm) {   // the convergence sums are fused into single-sweep launches only
+        if (k != 1) return cudaErrorInvalidValue;
+        if (method == HMI_HARMONIC) return launch_one<T, V, 1, HMI_HARMONIC, true>(a, st, nblocks_out);
+        if (method == HMI_CCST) return launch_one<T, V, 1, HMI_CCST, true>(a, st, nblocks_out);
+        return cudaErrorInvalidValue;
+    }
 #define HMI_CASE(M, KK) \
-    if (method == M && k == KK) return launch_one<T, V, KK, M>(a, st, nblocks_out);
+    if (method == M && k == KK) return launch_one<T, V, KK, M, false>(a, st, nblocks_out);
     HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 2) HMI_CASE(HMI_HARMONIC, 3)
     HMI_CASE(HMI_HARMONIC, 4) HMI_CASE(HMI_HARMONIC, 5) HMI_CASE(HMI_HARMONIC, 6)
     HMI_CASE(HMI_HARMONIC, 7) HMI_CASE(HMI_HARMONIC, 8)
