@@ -133,7 +133,7 @@ def run_reference(args):
         return
     img, mask = make_problem(GRID, GRID, np.float64)
     from oracle.fdpde_oracle import OracleInpainter
-    sweeps = 5                               # bounded sample per step
+    sweeps = 20                              # bounded sample per step (~0.1-0.5 s on the box)
     o = OracleInpainter("ccst", max_iters=sweeps, term_thres=1e-300, term_check_iters=10 ** 9, **CCST)
     for _ in range(args.warmup):
         o.inpaint_grid(img, mask)
