@@ -9,6 +9,7 @@
 
 #include "hmi_common.cuh"
 #include "hmi_stream.cuh"
+#include "hmi_stream_nl.cuh"
 
 namespace {
 
@@ -64,6 +65,7 @@ struct hmi_solver {
     double *h_result = nullptr;  // pinned
     int max_blocks = 0;
     bool use_stream = false;
+    bool use_nl = false;     // streaming kernel for TV / AMLE
     int tb = 1;              // sweeps fused per launch
     int chunk_rows = 0;      // 0 = auto
     int vec = 0;             // streaming kernel: cells per lane (0 = default)
@@ -82,7 +84,23 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
     const uint8_t *mask = s->mask + (long long)p.ghost_top * s->mpitch;
     int nblocks = 0;
     cudaError_t e;
-    if (s->use_stream) {
+    if (s->use_nl) {
+        if (k != 1) return fail(HMI_ERR_STATE, "the TV/AMLE kernel runs one sweep per launch");
+        hmi::NLLaunch<T> l;
+        memset(&l, 0, sizeof(l));
+        l.src = src; l.dst = dst; l.mask = mask;
+        l.pitch = s->pitch; l.mpitch = s->mpitch;
+        l.rows = p.rows; l.cols = p.cols;
+        l.row_lo = lo; l.row_hi = hi;
+        l.read_lo = -p.ghost_top; l.read_hi = p.rows + p.ghost_bottom;
+        l.top_border = p.ghost_top == 0; l.bottom_border = p.ghost_bottom == 0;
+        l.method = p.method; l.sgn = p.orientation;
+        l.chunk_rows = s->chunk_rows;
+        l.do_norm = do_norm ? 1 : 0;
+        l.dt = (T)p.dt; l.eps2 = (T)(p.epsilon * p.epsilon);
+        l.partials = s->d_partials; l.counter = s->d_counter; l.result = s->d_result;
+        e = hmi::launch_stream_nl<T>(l, st, &nblocks);
+    } else if (s->use_stream) {
         hmi::StreamArgs<T> a;
         memset(&a, 0, sizeof(a));
         a.src = src; a.dst = dst; a.mask = mask;
@@ -271,9 +289,10 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
                            p.border == HMI_BORDER_REFLECT101 && !(p.relaxation > 1.0);
     int tb = 1;
     bool use_stream = false;
-    if (p.kernel == HMI_KERNEL_STREAM && !stream_ok) {
+    bool use_nl = false;     // streaming kernel for TV / AMLE
+    if (p.kernel == HMI_KERNEL_STREAM && !stream_ok && (p.method == HMI_HARMONIC || p.method == HMI_CCST)) {
         delete s;
-        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel covers harmonic/ccst with reflect-101 borders and no over-relaxation");
+        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel needs reflect-101 borders and no over-relaxation");
     }
     if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
         const int maxk = hmi::stream_max_k(p.method, p.dtype);
@@ -292,6 +311,14 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     }
     s->use_stream = use_stream;
     s->tb = tb;
+    // TV / AMLE: single-sweep streaming kernel (reflect-101, no over-relaxation, grid not tiny)
+    const bool nl_ok = (p.method == HMI_TV || p.method == HMI_AMLE) && p.border == HMI_BORDER_REFLECT101 &&
+                       !(p.relaxation > 1.0) && p.rows >= 8 && p.cols >= 8;
+    if (p.kernel == HMI_KERNEL_STREAM && (p.method == HMI_TV || p.method == HMI_AMLE) && !nl_ok) {
+        delete s;
+        return fail(HMI_ERR_UNSUPPORTED, "streaming TV/AMLE kernel needs reflect-101 borders, no over-relaxation and a grid of at least 8x8");
+    }
+    s->use_nl = nl_ok && p.kernel != HMI_KERNEL_GENERIC;
 
     const int mb_gen = hmi::generic_max_blocks(s->phys_rows, p.cols);
     const int mb_str = hmi::stream_max_blocks(p.method, s->phys_rows, p.cols);
@@ -508,6 +535,9 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes)
 
 int hmi_temporal_block(const hmi_solver *s) { return s ? s->tb : 0; }
 int64_t hmi_launch_count(const hmi_solver *s) { return s ? s->launches : 0; }
-const char *hmi_kernel_name(const hmi_solver *s) { return !s ? "" : (s->use_stream ? "stream" : "generic"); }
+const char *hmi_kernel_name(const hmi_solver *s)
+{
+    return !s ? "" : (s->use_nl ? "stream_nl" : (s->use_stream ? "stream" : "generic"));
+}
 
 }  // extern "C"

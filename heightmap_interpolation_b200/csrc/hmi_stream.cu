@@ -26,51 +26,9 @@
 //     warp shuffles + one block reduction + a fixed-order final fold (no extra pass over the grid).
 #include "hmi_common.cuh"
 #include "hmi_stream.cuh"
+#include "hmi_stream_common.cuh"
 
 namespace hmi {
-
-template <typename T> struct Chunk16;
-template <> struct Chunk16<float> { typedef float4 type; static constexpr int N = 4; };
-template <> struct Chunk16<double> { typedef double2 type; static constexpr int N = 2; };
-
-__device__ __forceinline__ unsigned smem_u32(const void *p)
-{
-    return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(unsigned dst_smem, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <typename T>
-__device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
-template <typename T>
-__device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-
-template <int PH> struct Phase { static constexpr int value = PH; };
-
-__device__ __forceinline__ void lds16(unsigned addr, double (&v)[2])
-{
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
-}
-__device__ __forceinline__ void lds16(unsigned addr, float (&v)[4])
-{
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
-}
-__device__ __forceinline__ unsigned lds32(unsigned addr)
-{
-    unsigned r;
-    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(r) : "r"(addr));
-    return r;
-}
 
 // Geometry of one instantiation
 template <typename T, int V, int K, int METHOD>
@@ -412,7 +370,7 @@ int stream_max_blocks(int method, int rows_total, int cols)
 {
     // upper bound over every (V, K, chunk_rows) this file can launch: strips produce >= 32 columns,
     // chunks are >= 8 rows (callers clamp chunk_rows >= 8)
-    const long long nwin = (cols + 31) / 32 + 1;
+    const long long nwin = (cols + 31) / 32 + 3;
     const long long nch = (rows_total + 7) / 8 + 1;
     (void)method;
     return (int)((nwin * nch + 3) / 4 + 1);

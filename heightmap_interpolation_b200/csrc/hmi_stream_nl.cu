@@ -1,0 +1,374 @@
+// Streaming single-sweep kernel for the two non-linear, one-sided-difference methods: total
+// variation (tv_inpainter.py:20-33 + differential.py:146-187) and AMLE (amle_inpainter.py:41-59),
+// under the reflect-101 border rule.
+//
+// Same skeleton as hmi_stream.cu (one warp per strip, cp.async shared-memory ring, x-neighbours by
+// warp shuffles, y-neighbours in registers, interior/edge code paths, fused convergence sums), with
+// what the asymmetric schemes need on top:
+//   * Orientation by addressing.  The convolution-oriented scheme (convolver "masked*") is the
+//     point mirror of the correlation-oriented one (convolver "opencv"): the kernel always
+//     evaluates the s = +1 formulas of SURVEY.md A.3 in *canonical* coordinates and, for s = -1,
+//     walks the rows bottom-up and the columns right-to-left (canonical j' = pitch-1-j, i' = rows-1-i).
+//   * Intermediate fields with their own border rule.  The reference filters every intermediate
+//     array (n = g/|g| for TV, ux/uy for AMLE) with reflect-101 applied to *that array*, which
+//     is not what a mirrored ghost of f gives for one-sided differences.  So the row of
+//     intermediates is a pipeline stage of its own (row y-1 is built when row y lands, row y-2
+//     is emitted), and the two places where the rule bites are overridden explicitly: the left
+//     neighbour of the first column is the value at column 1, the upper neighbour of the first
+//     row is the value at row 1.
+//   * One reciprocal square root per cell (rsqrt + multiplies) instead of the reference's sqrt and
+//     two divides: within a few ulp, far inside the 1e-10 / 1e-5 parity bars, and 3x fewer
+//     slow-path fp64 operations than the generic kernel, which evaluates the normalisation at the
+//     three cells a step touches.
+#include "hmi_stream_nl.cuh"
+#include "hmi_stream_common.cuh"
+
+namespace hmi {
+
+template <typename T, int V>
+struct GeoNL {
+    static constexpr int N = Chunk16<T>::N;
+    static constexpr int NCH = V / N;
+    static constexpr int HV = V;                        // one lane of halo per side
+    static constexpr int S = 32 * V - 2 * HV;
+    static constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
+    static constexpr int SLOT = ROW_BYTES + 128;
+    static_assert(V % N == 0 && NCH >= 1, "a lane moves whole 16-byte chunks");
+    static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
+};
+
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+
+// One warp, one strip, one chunk of rows, in canonical coordinates (see header).
+template <typename T, int V, int METHOD, int SGN, int D, bool EDGE, bool NORM>
+__device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const unsigned ring_s, const int lane,
+                                               const int win, const int chunk, double &n_d2, double &n_f2,
+                                               double &n_mx, double &n_nan)
+{
+    typedef GeoNL<T, V> G;
+    typedef typename Chunk16<T>::type C16;
+    constexpr int N = G::N, NCH = G::NCH, HV = G::HV, S = G::S, ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT;
+    constexpr bool TV = (METHOD == HMI_TV);
+    constexpr unsigned VMASK = (1u << V) - 1u;
+    constexpr int LAG = 2;                             // step y emits row y-2
+
+    const int x0 = a.cbase + win * S - HV;             // canonical column of lane 0, cell 0
+    const int col0 = x0 + lane * V;                    // canonical column of this lane's cell 0
+    const int acol = SGN > 0 ? col0 : (int)a.pitch - col0 - V;   // actual column of the lane's chunk
+    const int y0 = a.row_lo + chunk * a.chunk_rows;    // canonical rows [y0, y1) are emitted
+    const int y1 = min(a.row_hi, y0 + a.chunk_rows);
+    const int ybeg = y0 - 1, yend = y1 + 1;            // canonical rows fetched: [ybeg, yend)
+    const int ystop = y1 + LAG;                        // steps: [ybeg, ystop)
+    const bool out_lane = (lane >= 1) && (lane < 31) && (col0 < a.chi) && (col0 + V > a.clo);
+    const T dt = a.dt;
+    const int rtop = a.top_border ? 0 : -0x40000000;   // canonical row whose upper neighbour is row 1
+
+    const int mcol = acol & ~3;
+    const unsigned msh = (unsigned)(acol & 3) * 8u;
+    const bool f_copies = EDGE ? ((acol >= 0) && (acol + V <= (int)a.pitch)) : true;
+    const bool m_copies = EDGE ? ((mcol >= 0) && (mcol + 4 <= (int)a.mpitch)) : true;
+
+    const unsigned ring_f = ring_s + lane * 16;
+    const unsigned ring_m = ring_s + ROW_BYTES + lane * 4;
+    const T *gbase = a.src + acol;
+    const uint8_t *mbase = a.mask + mcol;
+    const long long rstep = SGN > 0 ? a.pitch : -a.pitch;        // actual-row stride of a canonical step
+    const long long mstep = SGN > 0 ? a.mpitch : -a.mpitch;
+    auto arow = [&](int yc) { return SGN > 0 ? yc : a.rows - 1 - yc; };
+
+    int ynext = ybeg;
+    unsigned wofs = 0;
+    const T *gnext = gbase + (long long)arow(ybeg) * a.pitch;
+    const uint8_t *mnext = mbase + (long long)arow(ybeg) * a.mpitch;
+
+    auto issue = [&]() {
+        if (ynext < yend) {
+            const T *prow = gnext;
+            const uint8_t *mrow = mnext;
+            if (EDGE) {                                // reflect-101 at the global edges, clamp to memory
+                int ry = ynext;
+                if (ry < 0 && a.top_border) ry = -ry;
+                else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
+                ry = max(a.read_lo, min(a.read_hi - 1, ry));
+                prow = gbase + (long long)arow(ry) * a.pitch;
+                mrow = mbase + (long long)arow(ry) * a.mpitch;
+            }
+            if (f_copies) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + wofs + c * 512, prow + c * N);
+            }
+            if (m_copies) cp_async4(ring_m + wofs, mrow);
+        }
+        cp_async_commit();
+        ++ynext;
+        if (!EDGE) { gnext += rstep; mnext += mstep; }
+        wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
+    };
+
+#pragma unroll
+    for (int u = 0; u < D - 1; ++u) issue();
+
+    // f rows y-3, y-2, y-1 with the lane halos of rows y-2 and y-1; intermediates of rows y-2, y-3
+    T fA[V], fB[V], fC[V], L1 = T(0), R1 = T(0), L2 = T(0), R2 = T(0);
+    T P2[V], Q2[V], P3[V], Q3[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) fA[v] = fB[v] = fC[v] = P2[v] = Q2[v] = P3[v] = Q3[v] = T(0);
+    unsigned mhist = 0u;
+    unsigned rofs = 0;
+    T *dptr = a.dst + (long long)arow(ybeg - LAG) * a.pitch + acol;
+
+    for (int y = ybeg; y < ystop; ++y) {
+        cp_async_wait<D - 2>();
+        if (EDGE) __syncwarp();
+        T cur[V];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            T e[N];
+            lds16(ring_f + rofs + c * 512, e);
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                const int act = c * N + q;             // actual element -> canonical cell
+                cur[SGN > 0 ? act : V - 1 - act] = e[q];
+            }
+        }
+        unsigned mb;                                   // canonical cell v -> bit V-1-v
+        {
+            const unsigned w = lds32(ring_m + rofs);
+            if (V == 4) mb = (w * (SGN > 0 ? 0x08040201u : 0x01020408u)) >> 24;
+            else mb = ((((w >> msh) & 0xffffu) * (SGN > 0 ? 0x0201u : 0x0102u)) >> 8) & 3u;
+        }
+        if (EDGE) {
+            mb &= VMASK;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int c = col0 + v;
+                if (c < a.clo || c >= a.chi) {         // ghost column: value and mask of the mirror cell
+                    const int cm = (c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c;
+                    const int pos = max(0, min(32 * V - 1, cm - x0));
+                    const int pl = pos / V, pv = pos % V;
+                    const int pact = SGN > 0 ? pv : V - 1 - pv;            // actual element in lane pl
+                    T e[N];
+                    lds16(ring_s + rofs + (pact / N) * 512 + pl * 16, e);
+                    T val = e[0];
+#pragma unroll
+                    for (int j = 1; j < N; ++j) if ((pact % N) == j) val = e[j];
+                    cur[v] = val;
+                    const int pacol = SGN > 0 ? x0 + pl * V : (int)a.pitch - (x0 + pl * V) - V;
+                    const int pcol = SGN > 0 ? x0 + pos : (int)a.pitch - 1 - (x0 + pos);
+                    const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
+                    const unsigned kb = (w >> (8 * (pcol - (pacol & ~3)))) & 1u;
+                    mb = (mb & ~(1u << (V - 1 - v))) | (kb << (V - 1 - v));
+                }
+            }
+        }
+        mhist = (mhist << V) | mb;
+        rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
+        issue();
+
+        const T cl = shfl_up1(cur[V - 1]), cr = shfl_down1(cur[0]);
+
+        // ---- intermediates of row y-1 (centre fC, row below = cur)
+        T P1[V], Q1[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T right = (v < V - 1) ? fC[v + 1] : R1;
+            const T dx = right - fC[v];                // f[i, j+1] - f[i, j]
+            const T dy = cur[v] - fC[v];               // f[i+1, j] - f[i, j]
+            if (TV) {
+                const T inv = rsqrt_t(dx * dx + dy * dy + a.eps2);
+                P1[v] = dx * inv;                      // n_x
+                Q1[v] = dy * inv;                      // n_y
+            } else {
+                P1[v] = dy;                            // ux (reference's "x" is the row direction)
+                Q1[v] = dx;                            // uy
+            }
+        }
+
+        // ---- emit row r = y-2 (centre fB)
+        const int r = y - LAG;
+        const bool top = (r == rtop);
+        T Pl = shfl_up1(P2[V - 1]);
+        T Ql = TV ? T(0) : shfl_up1(Q2[V - 1]);
+        T Pr = T(0), Qr = T(0);
+        if (EDGE) { Pr = shfl_down1(P2[0]); if (!TV) Qr = shfl_down1(Q2[0]); }
+        const unsigned kb = (mhist >> (LAG * V)) & VMASK;
+        T res[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            T pl = (v > 0) ? P2[v - 1] : Pl;
+            T ql = (v > 0) ? Q2[v - 1] : Ql;
+            if (EDGE && col0 + v == a.clo) {           // reflect-101 of the intermediate: [-1] := [1]
+                pl = (v < V - 1) ? P2[v + 1] : Pr;
+                ql = (v < V - 1) ? Q2[v + 1] : Qr;
+            }
+            const T pu = top ? P1[v] : P3[v];
+            const T qu = top ? Q1[v] : Q3[v];
+            T step;
+            if (TV) {
+                step = (P2[v] - pl) + (Q2[v] - qu);
+            } else {
+                const T uxx = P2[v] - pu, uxy = P2[v] - pl, uyx = Q2[v] - qu, uyy = Q2[v] - ql;
+                T v0 = fC[v] - fA[v];
+                const T fl = (v > 0) ? fB[v - 1] : L2, fr = (v < V - 1) ? fB[v + 1] : R2;
+                T v1 = fr - fl;
+                const T inv = rsqrt_t(v0 * v0 + v1 * v1 + T(1e-15));
+                v0 *= inv;
+                v1 *= inv;
+                step = (uxx * v0) * v0 + (uyy * v1) * v1 + ((uxy + uyx) * v0) * v1;
+            }
+            const T c = fB[v];
+            const T cand = c + dt * step;
+            res[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
+        }
+        if (NORM) {
+            if (out_lane && r >= y0 && r < y1 && r >= 0 && r < a.rows) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if (col0 + v >= a.clo && col0 + v < a.chi) {
+                        const double dd = (double)(T)(res[v] - fB[v]);
+                        n_d2 += dd * dd;
+                        n_f2 += (double)res[v] * (double)res[v];
+                        const double ad = fabs(dd);
+                        if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
+                    }
+                }
+            }
+        }
+        if (out_lane && r >= y0 && r < y1) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                C16 t;
+                T *e = reinterpret_cast<T *>(&t);
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    const int act = c * N + q;
+                    e[q] = res[SGN > 0 ? act : V - 1 - act];
+                }
+                reinterpret_cast<C16 *>(dptr)[c] = t;
+            }
+        }
+        dptr += rstep;
+
+        // ---- rotate
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            fA[v] = fB[v]; fB[v] = fC[v]; fC[v] = cur[v];
+            P3[v] = P2[v]; Q3[v] = Q2[v]; P2[v] = P1[v]; Q2[v] = Q1[v];
+        }
+        L2 = L1; R2 = R1; L1 = cl; R1 = cr;
+    }
+    cp_async_wait<0>();
+}
+
+template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM>
+__global__ void __launch_bounds__(WPB * 32) stream_nl_kernel(const StreamNLArgs<T> a)
+{
+    typedef GeoNL<T, V> G;
+    extern __shared__ __align__(16) unsigned char ring_all[];
+    __shared__ double sh[NORM ? 128 : 1];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * D * G::SLOT;
+    const long long gw = (long long)blockIdx.x * WPB + wib;
+    const int win = (int)(gw % a.nwin);
+    const int chunk = (int)(gw / a.nwin);
+    double n_d2 = 0.0, n_f2 = 0.0, n_mx = 0.0, n_nan = 0.0;
+
+    if (chunk < a.nchunks) {
+        const int x0 = a.cbase + win * G::S - G::HV;
+        const int y0 = a.row_lo + chunk * a.chunk_rows;
+        const int y1 = min(a.row_hi, y0 + a.chunk_rows);
+        const bool col_edge = (x0 < a.clo) || (x0 + 32 * V > a.chi);
+        const bool row_edge = (y0 - 1 < 0 && a.top_border) || (y1 + 1 > a.rows && a.bottom_border) ||
+                              (y0 - 1 < a.read_lo) || (y1 + 1 > a.read_hi) || (y0 <= 0 && a.top_border);
+        if (col_edge || row_edge)
+            stream_rows_nl<T, V, METHOD, SGN, D, true, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+        else
+            stream_rows_nl<T, V, METHOD, SGN, D, false, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+    }
+    if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+template <typename T, int V, int METHOD, int SGN, bool NORM>
+static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nblocks_out)
+{
+    typedef GeoNL<T, V> G;
+    constexpr int D = 8, WPB = 4;
+    constexpr size_t SMEM = (size_t)WPB * D * G::SLOT;
+    StreamNLArgs<T> a;
+    a.src = l.src; a.dst = l.dst; a.mask = l.mask;
+    a.pitch = l.pitch; a.mpitch = l.mpitch;
+    a.rows = l.rows;
+    a.dt = l.dt; a.eps2 = l.eps2;
+    a.partials = l.partials; a.counter = l.counter; a.result = l.result;
+    // canonical frame: identity for s = +1, point mirror (rows-1-i, pitch-1-j) for s = -1
+    if (SGN > 0) {
+        a.clo = 0; a.chi = l.cols;
+        a.row_lo = l.row_lo; a.row_hi = l.row_hi;
+        a.read_lo = l.read_lo; a.read_hi = l.read_hi;
+        a.top_border = l.top_border; a.bottom_border = l.bottom_border;
+    } else {
+        a.clo = (int)l.pitch - l.cols; a.chi = (int)l.pitch;
+        a.row_lo = l.rows - l.row_hi; a.row_hi = l.rows - l.row_lo;
+        a.read_lo = l.rows - l.read_hi; a.read_hi = l.rows - l.read_lo;
+        a.top_border = l.bottom_border; a.bottom_border = l.top_border;
+    }
+    a.cbase = a.clo - (a.clo % V);
+    a.nwin = (a.chi - a.cbase + G::S - 1) / G::S;
+    const int nrows = a.row_hi - a.row_lo;
+    a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
+    a.nchunks = (nrows + a.chunk_rows - 1) / a.chunk_rows;
+    const long long warps = (long long)a.nwin * a.nchunks;
+    const int blocks = (int)((warps + WPB - 1) / WPB);
+    if (nblocks_out) *nblocks_out = blocks;
+    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<blocks, WPB * 32, SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+int stream_nl_auto_chunk_rows(int nrows, int nwin)
+{
+    const long long target_warps = 148LL * 16 * 2;
+    long long chunks = (target_warps + nwin - 1) / nwin;
+    if (chunks < 1) chunks = 1;
+    long long ch = (nrows + chunks - 1) / chunks;
+    if (ch < 24) ch = 24;
+    if (ch > nrows) ch = nrows;
+    if (ch < 1) ch = 1;
+    return (int)ch;
+}
+
+template <typename T, int V>
+static cudaError_t launch_nl_v(const NLLaunch<T> &l, cudaStream_t st, int *nb)
+{
+#define HMI_NL(M, SG)                                                              \
+    if (l.method == M && l.sgn == SG)                                              \
+        return l.do_norm ? launch_nl_one<T, V, M, SG, true>(l, st, nb)             \
+                         : launch_nl_one<T, V, M, SG, false>(l, st, nb);
+    HMI_NL(HMI_TV, 1) HMI_NL(HMI_TV, -1) HMI_NL(HMI_AMLE, 1) HMI_NL(HMI_AMLE, -1)
+#undef HMI_NL
+    return cudaErrorInvalidValue;
+}
+
+template <>
+cudaError_t launch_stream_nl<float>(const NLLaunch<float> &l, cudaStream_t st, int *nb)
+{
+    return launch_nl_v<float, 4>(l, st, nb);
+}
+template <>
+cudaError_t launch_stream_nl<double>(const NLLaunch<double> &l, cudaStream_t st, int *nb)
+{
+    return launch_nl_v<double, 2>(l, st, nb);
+}
+
+}  // namespace hmi

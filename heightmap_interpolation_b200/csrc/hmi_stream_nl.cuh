@@ -1,0 +1,51 @@
+// Interface of the streaming kernel for TV and AMLE (hmi_stream_nl.cu).
+#pragma once
+
+#include "hmi_common.cuh"
+
+namespace hmi {
+
+// What the host passes (actual coordinates)
+template <typename T>
+struct NLLaunch {
+    const T *src;
+    T *dst;
+    const uint8_t *mask;
+    long long pitch, mpitch;
+    int rows, cols;
+    int row_lo, row_hi;          // rows written [row_lo, row_hi)
+    int read_lo, read_hi;        // rows that exist in memory
+    int top_border, bottom_border;
+    int method;                  // HMI_TV or HMI_AMLE
+    int sgn;                     // +1 correlation ("opencv"), -1 convolution ("masked*")
+    int chunk_rows;              // <= 0 = auto
+    int do_norm;
+    T dt, eps2;
+    double *partials;
+    unsigned int *counter;
+    double *result;
+};
+
+// What the kernel sees (canonical coordinates: identity for sgn = +1, point mirror for sgn = -1)
+template <typename T>
+struct StreamNLArgs {
+    const T *src;
+    T *dst;
+    const uint8_t *mask;
+    long long pitch, mpitch;
+    int rows;                    // interior rows of the slab (for the row mirror)
+    int clo, chi, cbase;         // canonical column range of the grid, first strip's origin
+    int row_lo, row_hi, read_lo, read_hi, top_border, bottom_border;   // canonical
+    int chunk_rows, nwin, nchunks;
+    T dt, eps2;
+    double *partials;
+    unsigned int *counter;
+    double *result;
+};
+
+template <typename T>
+cudaError_t launch_stream_nl(const NLLaunch<T> &l, cudaStream_t st, int *nblocks_out);
+
+int stream_nl_auto_chunk_rows(int nrows, int nwin);
+
+}  // namespace hmi

@@ -176,6 +176,23 @@ def test_stream_kernel_matches_oracle(method, tb, dt, vec):
     assert err <= (1e-13 if dt == "f64" else 2e-6), (method, tb, dt, err)
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("conv", ["opencv", "masked"])
+@pytest.mark.parametrize("method", ["tv", "amle"])
+@pytest.mark.parametrize("shape", [(211, 333), (64, 61), (40, 1030), (515, 70)])
+def test_tv_amle_stream_kernel_matches_oracle(method, conv, dt, shape):
+    """Both orientations, ragged strips/chunks, unknown cells on every edge and corner."""
+    img, mask = _problem(shape[0], shape[1], DTYPES[dt])
+    K = 5
+    for chunk in (0, 29):
+        got, info = gpu_sweeps(method, conv, img, mask, K, kernel="stream", chunk_rows=chunk)
+        assert info[0] == "stream_nl" and info[2] == K
+        ref = oracle_sweeps(method, conv, img, mask, K)
+        assert np.array_equal(got[mask], img[mask])
+        err = range_err(got, ref)
+        assert err <= (1e-12 if dt == "f64" else 5e-6), (method, conv, dt, shape, chunk, err)
+
+
 @pytest.mark.parametrize("shape", [(64, 64), (130, 120), (97, 1031), (1031, 97), (512, 512)])
 def test_stream_kernel_shapes_and_chunking(shape):
     img, mask = _problem(shape[0], shape[1], np.float64)
@@ -222,7 +239,8 @@ def test_nan_never_converges_and_all_known_grid_is_identity():
 # ------------------------------------------------------------------ slabs with ghost rows (multi-GPU data path on one GPU)
 @pytest.mark.parametrize("method,kernel,block", [("harmonic", "stream", 4), ("ccst", "stream", 2),
                                                  ("tv", "generic", 3), ("amle", "generic", 2),
-                                                 ("ccst", "generic", 2)])
+                                                 ("ccst", "generic", 2), ("tv", "stream", 3),
+                                                 ("amle", "stream", 2)])
 def test_two_slabs_with_halo_exchange_equal_one_grid(method, kernel, block):
     """Row-slab decomposition: two solvers with ghost rows, halos copied by the test between
     temporal blocks, must reproduce the single-grid result exactly (same kernels, same order)."""

@@ -54,9 +54,7 @@ def main():
         for method in a.methods.split(","):
             code, step = M[method]
             for kernel in a.kernels.split(","):
-                if kernel == "stream" and method in ("tv", "amle"):
-                    continue
-                tbs = [int(t) for t in a.tbs.split(",")] if kernel == "stream" else [1]
+                tbs = [int(t) for t in a.tbs.split(",")] if (kernel == "stream" and method not in ("tv", "amle")) else [1]
                 for tb in tbs:
                     if kernel == "stream" and method == "ccst" and tb > 4:
                         continue
@@ -67,7 +65,7 @@ def main():
                         with Solver(p) as s:
                             if ch:
                                 s.set_option("chunk_rows", ch)
-                            if kernel == "stream":
+                            if kernel == "stream" and method not in ("tv", "amle"):
                                 s.set_option("vec", sk)
                             s.set_problem_host(img, mask)
                             nsw = a.sweeps if kernel == "stream" else max(4, a.sweeps // 4)
