@@ -345,14 +345,16 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
 
 int stream_auto_chunk_rows(int nrows, int nwin, int halo)
 {
-    // enough warps for ~2 waves of 16 warps on each of the 148 SMs, but chunks tall enough that the
-    // 2*halo redundant rows stay a small fraction
-    const long long target_warps = 148LL * 16 * 2;
-    long long chunks = (target_warps + nwin - 1) / nwin;
-    if (chunks < 1) chunks = 1;
-    long long ch = (nrows + chunks - 1) / chunks;
-    const long long min_ch = 12LL * halo;
-    if (ch < min_ch) ch = min_ch;
+    // Measured on B200 (profiles/r01_tune*.log): short chunks keep the warps that run together in
+    // one band of rows (DRAM/L2 locality) and give small grids several waves; chunks shorter than
+    // ~10x the halo pay for the 2*halo redundant rows.  Aim at ~4 waves of 16 warps per SM, within
+    // [max(64, 10*halo), 192] rows.
+    const long long target_warps = 148LL * 16 * 4;
+    long long ch = ((long long)nrows * nwin + target_warps - 1) / target_warps;
+    long long lo = 10LL * halo;
+    if (lo < 64) lo = 64;
+    if (ch < lo) ch = lo;
+    if (ch > 192) ch = 192;
     if (ch > nrows) ch = nrows;
     if (ch < 1) ch = 1;
     return (int)ch;

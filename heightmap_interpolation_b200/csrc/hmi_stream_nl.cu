@@ -338,11 +338,11 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
 
 int stream_nl_auto_chunk_rows(int nrows, int nwin)
 {
-    const long long target_warps = 148LL * 16 * 2;
-    long long chunks = (target_warps + nwin - 1) / nwin;
-    if (chunks < 1) chunks = 1;
-    long long ch = (nrows + chunks - 1) / chunks;
-    if (ch < 24) ch = 24;
+    // same rule as stream_auto_chunk_rows with a one-row halo: ~4 waves, within [32, 192] rows
+    const long long target_warps = 148LL * 16 * 4;
+    long long ch = ((long long)nrows * nwin + target_warps - 1) / target_warps;
+    if (ch < 32) ch = 32;
+    if (ch > 192) ch = 192;
     if (ch > nrows) ch = nrows;
     if (ch < 1) ch = 1;
     return (int)ch;
