@@ -210,11 +210,14 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
 #pragma unroll
         for (int s = 0; s < K; ++s) {
             const T(&rin)[V] = F[s][IN];           // newest row of this stage's input field
-            const T nl = shfl_up1(rin[V - 1]), nr = shfl_down1(rin[0]);   // its halos, for next step
             T o[V];
             const unsigned kb = (unsigned)(mhist >> ((R * s + R) * V)) & VMASK;
             T s4[V];
             sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
+            // halos of the newest row, for the next step; issued after the last use of the old
+            // ones so the shuffles can land in the same registers
+            FL[s] = shfl_up1(rin[V - 1]);
+            FR[s] = shfl_down1(rin[0]);
             if (!CC) {
                 // centre row F[s][IC] (row y-s-1), above F[s][IU], below rin
 #pragma unroll
@@ -227,15 +230,15 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                 // rin is row yy = y-2s of sweep s; hN = L f (row yy-1); output = sweep s+1 of row yy-2
 #pragma unroll
                 for (int v = 0; v < V; ++v) Hh[s][IN][v] = s4[v] - T(4) * F[s][IC][v];
-                const T hl = shfl_up1(Hh[s][IN][V - 1]), hr = shfl_down1(Hh[s][IN][0]);
                 sum4_row<T, V>(Hh[s][IU], Hh[s][IC], Hh[s][IN], HL[s], HR[s], s4);
+                HL[s] = shfl_up1(Hh[s][IN][V - 1]);
+                HR[s] = shfl_down1(Hh[s][IN][0]);
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const T c = F[s][IU][v];
                     const T cand = (c + c2 * s4[v]) + c3 * Hh[s][IC][v];
                     o[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
                 }
-                HL[s] = hl; HR[s] = hr;
             }
             if (NORM) {
                 const int yo = y - LAG;
@@ -253,7 +256,6 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                     }
                 }
             }
-            FL[s] = nl; FR[s] = nr;
             if (s < K - 1) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) F[s + 1][IN][v] = o[v];
