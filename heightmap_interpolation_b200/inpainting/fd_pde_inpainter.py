@@ -82,6 +82,7 @@ class FDPDEInpainter(ABC):
         self.converged_ = None
         self.kernel_name_ = None
         self.launches_ = None
+        self.history_ = []          # (rows, cols, iterations) of every inpaint_grid call of the last inpaint()
 
     # ------------------------------------------------------------------ configuration
     def get_config(self):
@@ -133,6 +134,7 @@ class FDPDEInpainter(ABC):
         (:160-185): the caller's `image` is initialised IN PLACE, a new array is returned.
         `out` is an extension: a preallocated (e.g. pinned) array to receive the result."""
         self.print_msg("*** INPAINTING ***")
+        self.history_ = []
         if self.mgs_levels > 1:
             self.print_msg("* Using a multi-grid solver")
             from .multigrid import inpaint_multigrid
@@ -173,6 +175,7 @@ class FDPDEInpainter(ABC):
                 done, diff, conv = self._loop(s, params.criteria)
                 out = s.get_result_host(out)
                 self._record(done, diff, conv, s.kernel_name, s.launch_count)
+        self.history_.append((image.shape[0], image.shape[1], self.iterations_))
         if not self.converged_:
             print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
         return out

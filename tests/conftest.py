@@ -27,3 +27,8 @@ def golden_sweeps():
 @pytest.fixture(scope="session")
 def golden_converged():
     return np.load(os.path.join(GOLDEN, "converged.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_multigrid():
+    return np.load(os.path.join(GOLDEN, "multigrid.npz"))

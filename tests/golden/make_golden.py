@@ -201,6 +201,54 @@ def main():
                       max_iters=23)
     with open(os.path.join(HERE, "progress_stdout.txt"), "w") as fh:
         fh.write(buf.getvalue())
+
+    # ---------------------------------------------------------------- E. multigrid driver
+    rows, cols = 101, 131                      # odd sizes: ceil-halving and non-2x up-sampling
+    mask = edge_mask(rows, cols, 0.35, 31)
+    mask[40:62, 50:75] = False                 # a hole that needs the coarse levels
+    out = {"mask": mask}
+    meta = []
+    mg_cases = [("harmonic", "opencv", "f64", "relative", 1e-6, 3, 20, "zeros"),
+                ("ccst", "masked", "f64", "absolute_percent", 1e-6, 2, 20, "mean"),
+                ("harmonic", "opencv", "f32", "relative", 1e-5, 3, 20, "zeros"),
+                ("tv", "opencv", "f64", "relative", 1e-5, 4, 30, "zeros"),      # pyramid stops early
+                ("harmonic", "opencv", "f64", "relative", 1e-6, 2, 200, "zeros")]   # too small: single grid, NO init
+    for dt_name, dtype in (("f64", np.float64), ("f32", np.float32)):
+        img = surface(rows, cols, 13, dtype)
+        img[~mask] = 0
+        out["image__" + dt_name] = img
+    for idx, (method, conv, dt_name, crit, thres, levels, min_res, init) in enumerate(mg_cases):
+        opts = dict(METHOD_OPTS[method])
+        opts.update(convolver=conv, term_criteria=crit, term_thres=thres, term_check_iters=10,
+                    mgs_levels=levels, mgs_min_res=min_res, init_with=init, max_iters=20000)
+        inp = classes[method](**opts)
+        per_level = []
+        orig_grid = inp.inpaint_grid
+        orig_check = inp.term_check
+        state = {"n": 0}
+
+        def counting(f, fnew, _o=orig_check, _s=state):
+            _s["n"] += 1
+            return _o(f, fnew)
+
+        def grid(image, mask_, _o=orig_grid, _s=state, _pl=per_level):
+            _s["n"] = 0
+            r = _o(image, mask_)
+            _pl.append((image.shape[0], image.shape[1], (_s["n"] - 1) * 10 + 1))
+            return r
+        inp.term_check = counting
+        inp.inpaint_grid = grid
+        caller = out["image__" + dt_name].copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = inp.inpaint(caller, mask)
+        key = "mg%02d" % idx
+        out[key] = res
+        out[key + "_caller_after"] = caller
+        meta.append("|".join([key, method, conv, dt_name, crit, repr(thres), str(levels), str(min_res), init,
+                              repr(per_level), repr(float(inp.term_thres))]))
+        print(meta[-1])
+    out["meta"] = np.array(meta)
+    np.savez_compressed(os.path.join(HERE, "multigrid.npz"), **out)
     print("golden fixtures written to", HERE)
 
 

@@ -316,3 +316,31 @@ def test_full_size_properties_8192_fp32_tv():
     sub = ref[ya - Ya:ya - Ya + (yb - ya), xa - Xa:xa - Xa + (xb - xa)]
     if Ya > 0 and Xa > 0 and Yb < n and Xb < n:     # window away from the global border
         assert range_err(got[ya:yb, xa:xb], sub) <= TOL["f32"]
+
+
+# ------------------------------------------------------------------ multigrid driver
+def test_multigrid_matches_reference(golden_multigrid):
+    """Same pyramid, per-level iteration counts, result, write-through into the caller's array and
+    final term_thres as the reference's inpaint_multigrid (fd_pde_inpainter.py:187-279)."""
+    import ast
+    import contextlib
+    import io
+    g = golden_multigrid
+    mask = g["mask"]
+    for row in g["meta"]:
+        key, method, conv, dt, crit, thres, levels, min_res, init, per_level, final_thres = str(row).split("|")
+        opts = dict(METHOD_OPTS[method])
+        opts.update(convolver=conv, term_criteria=crit, term_thres=float(thres), term_check_iters=10,
+                    mgs_levels=int(levels), mgs_min_res=int(min_res), init_with=init, max_iters=20000)
+        inp = CLASSES[method](**opts)
+        caller = g["image__" + dt].copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = inp.inpaint(caller, mask)
+        want_levels = ast.literal_eval(per_level)
+        assert inp.history_ == want_levels, (key, inp.history_, want_levels)
+        ref = g[key]
+        assert got.dtype == ref.dtype
+        assert np.array_equal(got[mask], ref[mask]), key
+        assert range_err(got, ref) <= TOL[dt], (key, range_err(got, ref))
+        assert np.allclose(caller, g[key + "_caller_after"], rtol=0, atol=1e-9 if dt == "f64" else 1e-3), key
+        assert float(inp.term_thres) == pytest.approx(float(final_thres), rel=1e-6), key

@@ -243,3 +243,19 @@ def test_host_loop_check_cadence():
     # NaN never terminates (0/0 in the relative criterion)
     assert not (Norm(0.0, 0.0, 0.0, 0.0).diff(C.HMI_RELATIVE) < 1.0)
     assert np.isnan(Norm(0.0, 1.0, 3.0, 1.0).diff(C.HMI_ABSOLUTE))
+
+
+def test_bilinear_resize_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    from heightmap_interpolation_b200.inpainting.multigrid import halve_image, resize_bilinear
+    rng = np.random.default_rng(0)
+    for dt, tol in ((np.float64, 1e-13), (np.float32, 1e-6)):
+        for sh, dh in (((50, 64), (100, 128)), ((51, 66), (101, 131)), ((26, 33), (51, 66)), ((37, 53), (74, 105))):
+            src = (rng.standard_normal(sh) * 100).astype(dt)
+            want = cv2.resize(src, dsize=(dh[1], dh[0]))
+            got = resize_bilinear(src, dh[0], dh[1])
+            assert got.dtype == want.dtype
+            assert np.abs(got - want).max() <= tol * 300
+    a = np.arange(35.0).reshape(5, 7)
+    h = halve_image(a)
+    assert h.shape == (3, 4) and h.base is not None and h[1, 1] == a[2, 2]      # a view, like the reference
