@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sweeps", type=int, default=SWEEPS_PER_STEP, help="sweeps per step")
     ap.add_argument("--temporal-block", type=int, default=0, help="sweeps fused per launch (0 = auto)")
-    ap.add_argument("--exchange-every", type=int, default=8, help="sweeps between halo exchanges (N > 1)")
+    ap.add_argument("--exchange-every", type=int, default=12, help="sweeps between halo exchanges (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "hmi_common.cuh"
 #include "hmi_stream.cuh"
@@ -34,6 +36,83 @@ int fail(int code, const char *fmt, ...)
 
 long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// A small per-process cache of device allocations: the reference builds a fresh inpainter (and
+// fresh arrays) per work area (apps/interpolate_netcdf4.py:200), which on the device would mean a
+// cudaMalloc/cudaFree pair per 100+ MiB grid per call.  Freed blocks are kept (per device, exact
+// size match) up to a byte budget and handed back to the next solver.
+struct CachedBlock { int device; size_t bytes; void *ptr; };
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+size_t g_cache_bytes = 0;
+const size_t kCacheBudget = (size_t)24 << 30;   // bytes kept at most
+
+cudaError_t cached_malloc(int device, void **p, size_t bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size(); ++i)
+            if (g_cache[i].device == device && g_cache[i].bytes == bytes) {
+                *p = g_cache[i].ptr;
+                g_cache_bytes -= bytes;
+                g_cache.erase(g_cache.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {       // drop the cache and retry once
+        cudaGetLastError();
+        std::vector<CachedBlock> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            drop.swap(g_cache);
+            g_cache_bytes = 0;
+        }
+        for (auto &b : drop) cudaFree(b.ptr);
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+std::vector<double *> g_pinned;                 // recycled 4-double pinned result buffers
+
+double *pinned_get()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (!g_pinned.empty()) {
+            double *p = g_pinned.back();
+            g_pinned.pop_back();
+            return p;
+        }
+    }
+    double *p = nullptr;
+    if (cudaMallocHost((void **)&p, 8 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void pinned_put(double *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_pinned.push_back(p);
+}
+
+int g_cc_major[64] = {0};                       // compute capability major per device (0 = unknown)
+
+void cached_free(int device, void *p, size_t bytes)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (bytes >= ((size_t)1 << 20) && g_cache_bytes + bytes <= kCacheBudget && g_cache.size() < 64) {
+            g_cache.push_back({device, bytes, p});
+            g_cache_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
 // The streaming kernel packs four mask bytes with one multiply, which needs them to be exactly 0/1.
 __global__ void normalize_mask_kernel(uint8_t *m, size_t n)
 {
@@ -59,10 +138,12 @@ struct hmi_solver {
     char *buf[2] = {nullptr, nullptr};
     uint8_t *mask = nullptr;
     int cur = 0;
+    void *d_scratch = nullptr;   // one block: partials | result | counter
+    size_t scratch_bytes = 0;
     double *d_partials = nullptr;
     unsigned int *d_counter = nullptr;
     double *d_result = nullptr;
-    double *h_result = nullptr;  // pinned
+    double *h_result = nullptr;  // pinned, recycled
     int max_blocks = 0;
     bool use_stream = false;
     bool use_nl = false;     // streaming kernel for TV / AMLE
@@ -71,6 +152,7 @@ struct hmi_solver {
     int vec = 0;             // streaming kernel: cells per lane (0 = default)
     long long launches = 0;
     bool has_problem = false;
+    size_t grid_bytes = 0, mask_bytes = 0;
 };
 
 namespace {
@@ -205,13 +287,12 @@ void destroy(hmi_solver *s)
 {
     if (!s) return;
     cudaSetDevice(s->p.device);
-    cudaFree(s->buf[0]);
-    cudaFree(s->buf[1]);
-    cudaFree(s->mask);
-    cudaFree(s->d_partials);
-    cudaFree(s->d_counter);
-    cudaFree(s->d_result);
-    if (s->h_result) cudaFreeHost(s->h_result);
+    cudaDeviceSynchronize();                     // nothing may still be using the blocks we recycle
+    cached_free(s->p.device, s->buf[0], s->grid_bytes);
+    cached_free(s->p.device, s->buf[1], s->grid_bytes);
+    cached_free(s->p.device, s->mask, s->mask_bytes);
+    cached_free(s->p.device, s->d_scratch, s->scratch_bytes);
+    pinned_put(s->h_result);
     delete s;
 }
 
@@ -268,11 +349,14 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
     if (p.device < 0 || p.device >= ndev) return fail(HMI_ERR_BAD_ARG, "device %d out of range (%d devices)", p.device, ndev);
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, p.device));
-    if (prop.major != 10)
-        return fail(HMI_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
-                    p.device, prop.major, prop.minor);
+    if (p.device < 64 && g_cc_major[p.device] == 0) {
+        int major = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, p.device));
+        g_cc_major[p.device] = major;
+    }
+    if (p.device < 64 && g_cc_major[p.device] != 10)
+        return fail(HMI_ERR_NO_DEVICE, "device %d has compute capability %d.x; this library is built for sm_100a (B200) only",
+                    p.device, g_cc_major[p.device]);
     CUDA_TRY(cudaSetDevice(p.device));
 
     hmi_solver *s = new (std::nothrow) hmi_solver();
@@ -326,20 +410,27 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
 
     const size_t grid_bytes = (size_t)s->phys_rows * s->pitch * s->elem;
     const size_t mask_bytes = (size_t)s->phys_rows * s->mpitch;
+    s->grid_bytes = grid_bytes;
+    s->mask_bytes = mask_bytes;
     int rc = HMI_OK;
     do {
-        if ((e = cudaMalloc((void **)&s->buf[0], grid_bytes)) != cudaSuccess) break;
-        if ((e = cudaMalloc((void **)&s->buf[1], grid_bytes)) != cudaSuccess) break;
-        if ((e = cudaMalloc((void **)&s->mask, mask_bytes)) != cudaSuccess) break;
-        if ((e = cudaMalloc((void **)&s->d_partials, (size_t)s->max_blocks * 4 * sizeof(double))) != cudaSuccess) break;
-        if ((e = cudaMalloc((void **)&s->d_counter, sizeof(unsigned int))) != cudaSuccess) break;
-        if ((e = cudaMalloc((void **)&s->d_result, 4 * sizeof(double))) != cudaSuccess) break;
-        if ((e = cudaMallocHost((void **)&s->h_result, 4 * sizeof(double))) != cudaSuccess) break;
-        if ((e = cudaMemset(s->buf[0], 0, grid_bytes)) != cudaSuccess) break;
-        if ((e = cudaMemset(s->buf[1], 0, grid_bytes)) != cudaSuccess) break;
-        if ((e = cudaMemset(s->mask, 1, mask_bytes)) != cudaSuccess) break;
-        if ((e = cudaMemset(s->d_counter, 0, sizeof(unsigned int))) != cudaSuccess) break;
-        if ((e = cudaMemset(s->d_result, 0, 4 * sizeof(double))) != cudaSuccess) break;
+        if ((e = cached_malloc(p.device, (void **)&s->buf[0], grid_bytes)) != cudaSuccess) break;
+        if ((e = cached_malloc(p.device, (void **)&s->buf[1], grid_bytes)) != cudaSuccess) break;
+        if ((e = cached_malloc(p.device, (void **)&s->mask, mask_bytes)) != cudaSuccess) break;
+        {
+            const size_t part = (size_t)s->max_blocks * 4 * sizeof(double);
+            s->scratch_bytes = (size_t)round_up((long long)(part + 64), 1 << 20);
+            if ((e = cached_malloc(p.device, &s->d_scratch, s->scratch_bytes)) != cudaSuccess) break;
+            s->d_partials = (double *)s->d_scratch;
+            s->d_result = (double *)((char *)s->d_scratch + part);
+            s->d_counter = (unsigned int *)((char *)s->d_scratch + part + 4 * sizeof(double));
+        }
+        s->h_result = pinned_get();
+        if (!s->h_result) { e = cudaErrorMemoryAllocation; break; }
+        if ((e = cudaMemsetAsync(s->buf[0], 0, grid_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->buf[1], 0, grid_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->mask, 1, mask_bytes)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->d_result, 0, 4 * sizeof(double) + sizeof(unsigned int))) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
         rc = fail(HMI_ERR_CUDA, "device allocation failed (%zu bytes per grid): %s", grid_bytes, cudaGetErrorString(e));
@@ -530,6 +621,24 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes)
     if (!s || !mask_dev || !pitch_bytes) return fail(HMI_ERR_BAD_ARG, "null argument");
     *mask_dev = s->mask;
     *pitch_bytes = (size_t)s->mpitch;
+    return HMI_OK;
+}
+
+int hmi_release_cache(void)
+{
+    std::vector<CachedBlock> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        drop.swap(g_cache);
+        g_cache_bytes = 0;
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto &b : drop) {
+        cudaSetDevice(b.device);
+        cudaFree(b.ptr);
+    }
+    cudaSetDevice(prev);
     return HMI_OK;
 }
 

@@ -93,4 +93,25 @@ int hmi_host_known_mean(const void *image, const uint8_t *mask, int64_t n, int32
     return HMI_OK;
 }
 
+int hmi_host_prefault(void *buf, size_t bytes)
+{
+    // touch one byte per page from several threads, so a freshly allocated result array does not
+    // take its page faults one by one inside the device-to-host copy
+    if (!buf) return HMI_ERR_BAD_ARG;
+    const int64_t n = (int64_t)bytes;
+    const int nt = num_threads(n);
+    const int64_t per = ((n + nt - 1) / nt + 4095) / 4096 * 4096;
+    auto touch = [](volatile unsigned char *p, int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i += 4096) p[i] = 0;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const int64_t a = t * per, b = (a + per < n) ? a + per : n;
+        if (a < b) th.emplace_back(touch, (volatile unsigned char *)buf, a, b);
+    }
+    touch((volatile unsigned char *)buf, 0, per < n ? per : n);
+    for (auto &x : th) x.join();
+    return HMI_OK;
+}
+
 }  // extern "C"

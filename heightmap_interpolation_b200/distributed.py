@@ -51,15 +51,19 @@ class CudaSlabEngine:
         self.device = torch.device("cuda", params.device)
         self.typestr = "<f8" if params.dtype == C.HMI_F64 else "<f4"
         self.elem = 8 if params.dtype == C.HMI_F64 else 4
+        self._views = {}            # device pointer -> torch view (the solver ping-pongs two grids)
 
     def load(self, image, mask):
         self.solver.set_problem_host(image, mask)
 
     def _grid(self):
         ptr, pitch = self.solver.current_grid()
-        rows = self.solver.phys_rows
-        arr = _DevArray(ptr, (rows, pitch // self.elem), self.typestr)
-        return torch.as_tensor(arr, device=self.device)
+        t = self._views.get(ptr)
+        if t is None:
+            rows = self.solver.phys_rows
+            arr = _DevArray(ptr, (rows, pitch // self.elem), self.typestr)
+            t = self._views[ptr] = torch.as_tensor(arr, device=self.device)
+        return t
 
     def rows_view(self, lo, hi):
         """Physical rows [lo, hi) of the current iterate (row 0 = first ghost row), pitched."""

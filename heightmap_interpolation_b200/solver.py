@@ -122,6 +122,8 @@ class Solver:
         p = self.params
         if out is None:
             out = np.empty((p.rows, p.cols), dtype=self.np_dtype)
+            if out.nbytes >= (1 << 22):
+                self._lib.hmi_host_prefault(out.ctypes.data, out.nbytes)
         C.check(self._lib.hmi_get_result_host(self._h, out.ctypes.data, out.strides[0]))
         return out
 
@@ -165,6 +167,8 @@ def inpaint_host(params, image, mask, out=None):
         np.ascontiguousarray(mask, dtype=np.uint8)
     if out is None:
         out = np.empty_like(image)
+        if out.nbytes >= (1 << 22):
+            lib.hmi_host_prefault(out.ctypes.data, out.nbytes)
     elif out.shape != image.shape or out.dtype != image.dtype or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous array of the image's shape and dtype")
     st = C.HmiStatus()

@@ -161,6 +161,13 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes);
 int hmi_host_fill_unknown(void *image, const uint8_t *mask, int64_t n, int32_t dtype, double value);
 int hmi_host_known_mean(const void *image, const uint8_t *mask, int64_t n, int32_t dtype, double *mean);
 
+/* Pre-fault a freshly allocated host buffer with several threads (the result array of inpaint()). */
+int hmi_host_prefault(void *buf, size_t bytes);
+
+/* Device blocks of destroyed solvers are kept in a per-process cache (the reference builds a fresh
+ * inpainter per work area, apps/interpolate_netcdf4.py:200); this returns them to the driver. */
+int hmi_release_cache(void);
+
 /* Tuning knobs for tests and benchmarks: "chunk_rows" (rows per warp chunk of the streaming kernel,
  * 0 = auto) and "temporal_block" (sweeps fused per launch). */
 int hmi_set_option(hmi_solver *s, const char *key, int64_t value);
