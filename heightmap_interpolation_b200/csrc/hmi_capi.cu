@@ -150,6 +150,7 @@ struct hmi_solver {
     int tb = 1;              // sweeps fused per launch
     int chunk_rows = 0;      // 0 = auto
     int vec = 0;             // streaming kernel: cells per lane (0 = default)
+    int tma = 0;             // streaming kernel: TMA bulk-copy staging instead of cp.async
     long long launches = 0;
     bool has_problem = false;
     size_t grid_bytes = 0, mask_bytes = 0;
@@ -193,6 +194,7 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
         a.top_border = p.ghost_top == 0; a.bottom_border = p.ghost_bottom == 0;
         a.chunk_rows = s->chunk_rows;
         a.vec = s->vec;
+        a.tma = s->tma;
         a.dt = (T)p.dt; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
         a.do_norm = do_norm ? 1 : 0;
         a.partials = s->d_partials; a.counter = s->d_counter; a.result = s->d_result;
@@ -450,6 +452,10 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
     if (!strcmp(key, "chunk_rows")) {
         if (value < 0) return fail(HMI_ERR_BAD_ARG, "chunk_rows must be >= 0");
         s->chunk_rows = value == 0 ? 0 : (value < 8 ? 8 : (int)value);
+        return HMI_OK;
+    }
+    if (!strcmp(key, "tma")) {
+        s->tma = value ? 1 : 0;
         return HMI_OK;
     }
     if (!strcmp(key, "vec")) {

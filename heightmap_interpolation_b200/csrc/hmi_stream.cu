@@ -41,6 +41,10 @@ struct Geo {
     static constexpr int S = 32 * V - 2 * HV;           // columns a warp produces
     static constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
     static constexpr int SLOT = ROW_BYTES + 128;        // one row segment + one mask word per lane
+    // TMA staging: the row segment and the 16-byte-aligned superset of its mask bytes land as two
+    // bulk copies; D mbarriers per warp follow the ring
+    static constexpr int MB_T = ((32 * V + 16 + 15) / 16) * 16;
+    static constexpr int SLOT_T = ROW_BYTES + MB_T;
     static_assert(V % N == 0 && NCH >= 1, "a lane moves whole 16-byte chunks");
     static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
     static_assert(S > 0, "temporal block too deep for this strip width");
@@ -62,7 +66,7 @@ __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], cons
 // One warp streams its strip down one chunk of rows.  EDGE = the strip touches a grid edge (ghost
 // columns to mirror, rows to reflect or clamp); interior strips skip all of that and address
 // memory incrementally.  NORM = accumulate the convergence sums of the (single) sweep.
-template <typename T, int V, int K, int METHOD, int D, bool EDGE, bool NORM>
+template <typename T, int V, int K, int METHOD, int D, bool EDGE, bool NORM, bool TMA>
 __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsigned ring_s, const int lane,
                                             const int win, const int chunk, double &n_d2, double &n_f2,
                                             double &n_mx, double &n_nan)
@@ -70,7 +74,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     typedef Geo<T, V, K, METHOD> G;
     typedef typename Chunk16<T>::type C16;
     constexpr int N = G::N, NCH = G::NCH, R = G::R, H = G::H, HV = G::HV, S = G::S;
-    constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT;
+    constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = TMA ? G::SLOT_T : G::SLOT;
     constexpr bool CC = (METHOD == HMI_CCST);
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int LAG = H;                         // step y emits sweep K of row y - LAG
@@ -128,27 +132,64 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     const T *gnext = gbase + (long long)ybeg * a.pitch;        // interior path: incremental
     const uint8_t *mnext = mbase + (long long)ybeg * a.mpitch;
 
-    auto issue = [&]() {
-        if (ynext < yend) {
-            const T *prow = gnext;
-            const uint8_t *mrow = mnext;
-            if (EDGE) {                            // reflect-101 at global edges, clamp to memory
-                int ry = ynext;
-                if (ry < 0 && a.top_border) ry = -ry;
-                else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
-                ry = max(a.read_lo, min(a.read_hi - 1, ry));
-                prow = gbase + (long long)ry * a.pitch;
-                mrow = mbase + (long long)ry * a.mpitch;
-            }
-            if (f_copies) {
+    // TMA variant: lane 0 moves the whole row segment and its mask bytes with two bulk copies that
+    // complete on the slot's mbarrier
+    const unsigned bar_s = ring_s + D * SLOT;                  // D mbarriers after the ring
+    const int mx16 = x0 & ~15;                                 // mask copy starts 16-byte aligned
+    unsigned widx = 0;                                         // slot index being filled
+    if (TMA) {
+        if (lane == 0) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) cp_async16(ring_f + wofs + c * 512, prow + c * N);
-            }
-            if (m_copies) cp_async4(ring_m + wofs, mrow);
+            for (int i = 0; i < D; ++i) mbar_init(bar_s + 8 * i, 1);
+            mbar_fence_init();
         }
-        cp_async_commit();
+        __syncwarp();
+    }
+
+    auto issue = [&]() {
+        if (TMA) {
+            if (ynext < yend && lane == 0) {
+                int ry = ynext;
+                int c_lo = x0, c_hi = x0 + 32 * V, m_lo = mx16, m_hi = ((x0 + 32 * V + 15) & ~15);
+                if (EDGE) {
+                    if (ry < 0 && a.top_border) ry = -ry;
+                    else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
+                    ry = max(a.read_lo, min(a.read_hi - 1, ry));
+                    c_lo = max(c_lo, 0); c_hi = min(c_hi, (int)a.pitch);
+                    m_lo = max(m_lo, 0); m_hi = min(m_hi, (int)a.mpitch);
+                }
+                const unsigned bar = bar_s + 8 * widx;
+                const unsigned fb = (unsigned)(c_hi - c_lo) * (unsigned)sizeof(T), mbytes = (unsigned)(m_hi - m_lo);
+                fence_proxy_async();               // the slot's previous contents were read with ld.shared
+                mbar_expect_tx(bar, fb + mbytes);
+                tma_load_1d(ring_s + wofs + (unsigned)(c_lo - x0) * (unsigned)sizeof(T),
+                            a.src + (long long)ry * a.pitch + c_lo, fb, bar);
+                tma_load_1d(ring_s + wofs + ROW_BYTES + (unsigned)(m_lo - mx16),
+                            a.mask + (long long)ry * a.mpitch + m_lo, mbytes, bar);
+            }
+            widx = (widx + 1 == D) ? 0u : widx + 1;
+        } else {
+            if (ynext < yend) {
+                const T *prow = gnext;
+                const uint8_t *mrow = mnext;
+                if (EDGE) {                        // reflect-101 at global edges, clamp to memory
+                    int ry = ynext;
+                    if (ry < 0 && a.top_border) ry = -ry;
+                    else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
+                    ry = max(a.read_lo, min(a.read_hi - 1, ry));
+                    prow = gbase + (long long)ry * a.pitch;
+                    mrow = mbase + (long long)ry * a.mpitch;
+                }
+                if (f_copies) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) cp_async16(ring_f + wofs + c * 512, prow + c * N);
+                }
+                if (m_copies) cp_async4(ring_m + wofs, mrow);
+            }
+            cp_async_commit();
+            if (!EDGE) { gnext += a.pitch; mnext += a.mpitch; }
+        }
         ++ynext;
-        if (!EDGE) { gnext += a.pitch; mnext += a.mpitch; }
         wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
     };
 
@@ -156,26 +197,38 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     for (int u = 0; u < D - 1; ++u) issue();
 
     unsigned rofs = 0;                                         // ring byte offset of the slot to read
+    unsigned ridx = 0, rphase = 0;                             // TMA: slot index and mbarrier parity
     T *dptr = a.dst + (long long)(ybeg - LAG) * a.pitch + col0;   // row emitted by step ybeg
 
     auto step = [&](auto ph, const int y) {
         constexpr int PH = decltype(ph)::value;
         constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
-        cp_async_wait<D - 2>();                    // this lane's copies of row y have landed
-        if (EDGE) __syncwarp();                    // ... and the other lanes' (for the mirrors)
+        if (TMA) {
+            mbar_wait(bar_s + 8 * ridx, rphase);   // both bulk copies of row y have landed
+        } else {
+            cp_async_wait<D - 2>();                // this lane's copies of row y have landed
+            if (EDGE) __syncwarp();                // ... and the other lanes' (for the mirrors)
+        }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             T e[N];
-            lds16(ring_f + rofs + c * 512, e);
+            lds16(TMA ? ring_s + rofs + lane * (16 * NCH) + c * 16 : ring_f + rofs + c * 512, e);
 #pragma unroll
             for (int q = 0; q < N; ++q) F[0][IN][c * N + q] = e[q];
         }
         // mask bytes are 0/1: one multiply packs them into V bits, cell v -> bit V-1-v
         unsigned mb;
         {
-            const unsigned w = lds32(ring_m + rofs);
+            unsigned w, sh = msh;
+            if (TMA) {
+                const unsigned off = (unsigned)(x0 - mx16) + (unsigned)(V * lane);
+                w = lds32(ring_s + rofs + ROW_BYTES + (off & ~3u));
+                sh = (off & 3u) * 8u;
+            } else {
+                w = lds32(ring_m + rofs);
+            }
             if (V == 4) mb = (w * 0x08040201u) >> 24;
-            else mb = ((((w >> msh) & 0xffffu) * 0x0201u) >> 8) & 3u;
+            else mb = ((((w >> sh) & 0xffffu) * 0x0201u) >> 8) & 3u;
         }
         if (EDGE) {
             // Ghost columns take the value and mask of their mirror cell, which sits in this
@@ -189,21 +242,32 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                     const int cm = (c < 0) ? -c : 2 * (a.cols - 1) - c;
                     const int pos = max(0, min(32 * V - 1, cm - x0));
                     const int pl = pos / V, pq = pos % V;
-                    T e[N];
-                    lds16(ring_s + rofs + (pq / N) * 512 + pl * 16, e);
-                    T val = e[0];
+                    unsigned kb;
+                    if (TMA) {
+                        F[0][IN][q] = lds1(ring_s + rofs + (unsigned)pos * (unsigned)sizeof(T), T(0));
+                        kb = lds8(ring_s + rofs + ROW_BYTES + (unsigned)(x0 - mx16) + (unsigned)pos) & 1u;
+                    } else {
+                        T e[N];
+                        lds16(ring_s + rofs + (pq / N) * 512 + pl * 16, e);
+                        T val = e[0];
 #pragma unroll
-                    for (int j = 1; j < N; ++j) if ((pq % N) == j) val = e[j];
-                    F[0][IN][q] = val;
-                    const int pmcol = (x0 + pl * V) & ~3;
-                    const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
-                    const unsigned kb = (w >> (8 * (x0 + pos - pmcol))) & 1u;
+                        for (int j = 1; j < N; ++j) if ((pq % N) == j) val = e[j];
+                        F[0][IN][q] = val;
+                        const int pmcol = (x0 + pl * V) & ~3;
+                        const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
+                        kb = (w >> (8 * (x0 + pos - pmcol))) & 1u;
+                    }
                     mb = (mb & ~(1u << (V - 1 - q))) | (kb << (V - 1 - q));
                 }
             }
         }
         mhist = (mhist << V) | (unsigned long long)mb;
         rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
+        if (TMA) {
+            ridx = (ridx + 1 == D) ? 0u : ridx + 1;
+            if (ridx == 0) rphase ^= 1u;
+            __syncwarp();                          // every lane is done with the slot about to be refilled
+        }
         issue();                                   // refills the slot read one step ago
 
         T res[V];
@@ -284,18 +348,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         if (y + 1 < yend) step(Phase<1>(), y + 1);
         if (y + 2 < yend) step(Phase<2>(), y + 2);
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
 }
 
-template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM>
+template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM, bool TMA>
 __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs<T> a)
 {
     typedef Geo<T, V, K, METHOD> G;
-    extern __shared__ __align__(16) unsigned char ring_all[];
+    constexpr int WARP_RING = TMA ? ((D * G::SLOT_T + D * 8 + 15) / 16) * 16 : D * G::SLOT;
+    extern __shared__ __align__(128) unsigned char ring_all[];
     __shared__ double sh[NORM ? 128 : 1];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * D * G::SLOT;
+    const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * WARP_RING;
     const long long gw = (long long)blockIdx.x * WPB + wib;
     const int win = (int)(gw % a.nwin);
     const int chunk = (int)(gw / a.nwin);
@@ -310,9 +375,9 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
         const bool row_edge = (ybeg < 0 && a.top_border) || (yend > a.rows && a.bottom_border) ||
                               (ybeg < a.read_lo) || (yend > a.read_hi);
         if (col_edge || row_edge)
-            stream_rows<T, V, K, METHOD, D, true, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, true, NORM, TMA>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows<T, V, K, METHOD, D, false, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, false, NORM, TMA>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -320,12 +385,12 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
 // ------------------------------------------------------------------------------------------------
 // host side
 
-template <typename T, int V, int K, int METHOD, bool NORM>
+template <typename T, int V, int K, int METHOD, bool NORM, bool TMA>
 static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nblocks_out)
 {
     typedef Geo<T, V, K, METHOD> G;
     constexpr int D = 8, WPB = 4, MINB = 1;
-    constexpr size_t SMEM = (size_t)WPB * D * G::SLOT;
+    constexpr size_t SMEM = (size_t)WPB * (TMA ? ((D * G::SLOT_T + D * 8 + 15) / 16) * 16 : D * G::SLOT);
     StreamArgs<T> a = a0;
     a.nwin = (a.cols + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
@@ -334,7 +399,7 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
     const long long warps = (long long)a.nwin * a.nchunks;
     const int blocks = (int)((warps + WPB - 1) / WPB);
     if (nblocks_out) *nblocks_out = blocks;
-    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM>;
+    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM, TMA>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -380,17 +445,17 @@ int stream_max_blocks(int method, int rows_total, int cols)
     return (int)((nwin * nch + 3) / 4 + 1);
 }
 
-template <typename T, int V>
+template <typename T, int V, bool TMA>
 static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
 {
     if (a.do_norm) {   // the convergence sums are fused into single-sweep launches only
         if (k != 1) return cudaErrorInvalidValue;
-        if (method == HMI_HARMONIC) return launch_one<T, V, 1, HMI_HARMONIC, true>(a, st, nblocks_out);
-        if (method == HMI_CCST) return launch_one<T, V, 1, HMI_CCST, true>(a, st, nblocks_out);
+        if (method == HMI_HARMONIC) return launch_one<T, V, 1, HMI_HARMONIC, true, TMA>(a, st, nblocks_out);
+        if (method == HMI_CCST) return launch_one<T, V, 1, HMI_CCST, true, TMA>(a, st, nblocks_out);
         return cudaErrorInvalidValue;
     }
 #define HMI_CASE(M, KK) \
-    if (method == M && k == KK) return launch_one<T, V, KK, M, false>(a, st, nblocks_out);
+    if (method == M && k == KK) return launch_one<T, V, KK, M, false, TMA>(a, st, nblocks_out);
     HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 2) HMI_CASE(HMI_HARMONIC, 3)
     HMI_CASE(HMI_HARMONIC, 4) HMI_CASE(HMI_HARMONIC, 5) HMI_CASE(HMI_HARMONIC, 6)
     HMI_CASE(HMI_HARMONIC, 7) HMI_CASE(HMI_HARMONIC, 8)
@@ -402,14 +467,16 @@ static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStrea
 template <>
 cudaError_t launch_stream<float>(int method, int k, const StreamArgs<float> &a, cudaStream_t st, int *nblocks_out)
 {
-    return launch_v<float, 4>(method, k, a, st, nblocks_out);
+    if (a.tma) return launch_v<float, 4, true>(method, k, a, st, nblocks_out);
+    return launch_v<float, 4, false>(method, k, a, st, nblocks_out);
 }
 
 template <>
 cudaError_t launch_stream<double>(int method, int k, const StreamArgs<double> &a, cudaStream_t st, int *nblocks_out)
 {
-    if (a.vec == 4) return launch_v<double, 4>(method, k, a, st, nblocks_out);
-    return launch_v<double, 2>(method, k, a, st, nblocks_out);
+    if (a.vec == 4) return launch_v<double, 4, false>(method, k, a, st, nblocks_out);
+    if (a.tma) return launch_v<double, 2, true>(method, k, a, st, nblocks_out);
+    return launch_v<double, 2, false>(method, k, a, st, nblocks_out);
 }
 
 }  // namespace hmi

@@ -20,6 +20,7 @@ struct StreamArgs {
     int top_border, bottom_border;
     int chunk_rows;             // rows per warp chunk; <= 0 = auto
     int vec;                    // cells per lane (fp64: 2 or 4; 0 = default)
+    int tma;                    // 1 = stage rows with TMA bulk copies + mbarriers instead of cp.async
     int nwin, nchunks;          // filled by the launcher
     T dt, tension, one_minus_tension;
     int do_norm;

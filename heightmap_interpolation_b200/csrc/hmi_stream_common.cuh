@@ -48,5 +48,59 @@ __device__ __forceinline__ unsigned lds32(unsigned addr)
     return r;
 }
 
+__device__ __forceinline__ double lds1(unsigned addr, double)
+{
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds1(unsigned addr, float)
+{
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ unsigned lds8(unsigned addr)
+{
+    unsigned r;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(r) : "r"(addr));
+    return r;
+}
+
+// ---- TMA (bulk asynchronous copy) + mbarrier helpers ------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 
 }  // namespace hmi

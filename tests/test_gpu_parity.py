@@ -27,7 +27,7 @@ CONV = {"opencv": (1, C.HMI_BORDER_REFLECT101), "masked": (-1, C.HMI_BORDER_REFL
 
 
 def gpu_sweeps(method, conv, image, mask, K, kernel="auto", tb=0, chunk_rows=0, relaxation=0.0,
-               opts=None, want_norm=False, vec=None):
+               opts=None, want_norm=False, vec=None, tma=None):
     opts = dict(METHOD_OPTS[method]) if opts is None else opts
     o, b = CONV[conv]
     p = make_params(image.shape[0], image.shape[1], image.dtype, METHODS[method], orientation=o,
@@ -39,6 +39,8 @@ def gpu_sweeps(method, conv, image, mask, K, kernel="auto", tb=0, chunk_rows=0, 
             s.set_option("chunk_rows", chunk_rows)
         if vec is not None:
             s.set_option("vec", vec)
+        if tma is not None:
+            s.set_option("tma", tma)
         s.set_problem_host(image, mask)
         nm = None
         if want_norm:
@@ -158,17 +160,17 @@ def _problem(rows, cols, dtype, p=0.4, seed=3):
     return synthetic.zero_unknown(img, mask), mask
 
 
-@pytest.mark.parametrize("vec", [2, 4])
+@pytest.mark.parametrize("vec,tma", [(2, 0), (4, 0), (2, 1)])
 @pytest.mark.parametrize("dt", ["f64", "f32"])
 @pytest.mark.parametrize("method,tb", [("harmonic", 1), ("harmonic", 2), ("harmonic", 3),
                                        ("harmonic", 4), ("harmonic", 5), ("harmonic", 8),
                                        ("ccst", 1), ("ccst", 2), ("ccst", 3), ("ccst", 4)])
-def test_stream_kernel_matches_oracle(method, tb, dt, vec):
+def test_stream_kernel_matches_oracle(method, tb, dt, vec, tma):
     # odd sizes: ragged last strip, last chunk, columns not a multiple of the vector width
     img, mask = _problem(211, 333, DTYPES[dt])
     K = 2 * tb + 1                                    # two full blocks + a remainder block
     got, info = gpu_sweeps(method, "opencv", img, mask, K, kernel="stream", tb=tb, chunk_rows=37,
-                           vec=vec)
+                           vec=vec, tma=tma)
     assert info[0] == "stream" and info[1] == tb
     ref = oracle_sweeps(method, "opencv", img, mask, K)
     assert np.array_equal(got[mask], img[mask])
@@ -198,10 +200,10 @@ def test_stream_kernel_shapes_and_chunking(shape):
     img, mask = _problem(shape[0], shape[1], np.float64)
     ref = oracle_sweeps("ccst", "masked", img, mask, 6)
     for chunk in (0, 8, 50, 10 ** 6):
-        for vec in (2, 4):
+        for vec, tma in ((2, 0), (4, 0), (2, 1)):
             got, info = gpu_sweeps("ccst", "masked", img, mask, 6, kernel="stream", tb=2,
-                                   chunk_rows=chunk, vec=vec)
-            assert range_err(got, ref) <= 1e-13, (shape, chunk, vec)
+                                   chunk_rows=chunk, vec=vec, tma=tma)
+            assert range_err(got, ref) <= 1e-13, (shape, chunk, vec, tma)
 
 
 @pytest.mark.parametrize("dt", ["f64", "f32"])

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=48)
     ap.add_argument("--mask", default="tracks")
     ap.add_argument("--vecs", default="2,4")
+    ap.add_argument("--tma", type=int, default=0)
     a = ap.parse_args()
     n = a.n
     for dt in a.dtypes.split(","):
@@ -67,6 +68,7 @@ def main():
                                 s.set_option("chunk_rows", ch)
                             if kernel == "stream" and method not in ("tv", "amle"):
                                 s.set_option("vec", sk)
+                                s.set_option("tma", a.tma)
                             s.set_problem_host(img, mask)
                             nsw = a.sweeps if kernel == "stream" else max(4, a.sweeps // 4)
                             nsw = (nsw // tb) * tb
