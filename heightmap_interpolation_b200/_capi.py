@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libhmi_b200.so")
+LIB_PATH = os.environ.get("HMI_B200_LIB") or os.path.join(_HERE, "csrc", "libhmi_b200.so")
 
 HMI_F32, HMI_F64 = 0, 1
 HMI_HARMONIC, HMI_CCST, HMI_TV, HMI_AMLE = 0, 1, 2, 3

@@ -28,6 +28,17 @@
 #include "hmi_stream.cuh"
 #include "hmi_stream_common.cuh"
 
+// build-time tuning knobs (defaults measured on B200, see profiles/)
+#ifndef HMI_STREAM_RING
+#define HMI_STREAM_RING 8   // ring slots per warp
+#endif
+#ifndef HMI_STREAM_WPB
+#define HMI_STREAM_WPB 4    // warps per CTA
+#endif
+#ifndef HMI_STREAM_MINB
+#define HMI_STREAM_MINB 1   // __launch_bounds__ min CTAs per SM (1 = let ptxas choose)
+#endif
+
 namespace hmi {
 
 // Geometry of one instantiation
@@ -389,7 +400,7 @@ template <typename T, int V, int K, int METHOD, bool NORM, bool TMA>
 static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nblocks_out)
 {
     typedef Geo<T, V, K, METHOD> G;
-    constexpr int D = 8, WPB = 4, MINB = 1;
+    constexpr int D = HMI_STREAM_RING, WPB = HMI_STREAM_WPB, MINB = HMI_STREAM_MINB;
     constexpr size_t SMEM = (size_t)WPB * (TMA ? ((D * G::SLOT_T + D * 8 + 15) / 16) * 16 : D * G::SLOT);
     StreamArgs<T> a = a0;
     a.nwin = (a.cols + G::S - 1) / G::S;

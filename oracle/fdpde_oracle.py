@@ -110,6 +110,8 @@ class OracleInpainter:
         self.term_criteria = kwargs.pop("term_criteria", "relative")
         self.tension = kwargs.pop("tension", 0.0)
         self.epsilon = kwargs.pop("epsilon", 1e-2)
+        # amle_inpainter.py:26-37: scipy.ndimage.convolve1d (mode='reflect') on the whole grid
+        self.convolve_in_1d = kwargs.pop("convolve_in_1d", False)
         if self.convolver_type.lower() not in CONVOLVERS:
             raise ValueError("Unknown convolver type '{:s}'".format(self.convolver_type))
         # results of the last solve (the reference only prints these)
@@ -119,6 +121,8 @@ class OracleInpainter:
 
     def _params(self, term_thres, max_iters=None):
         o, b, m = CONVOLVERS[self.convolver_type.lower()]
+        if self.convolve_in_1d and self.method == "amle":
+            o, b, m = -1, 1, 0          # true convolution, symmetric border, whole grid
         crit = CRITERIA.get(self.term_criteria, -1)
         if crit < 0:
             raise ValueError("Unknown termination criteria!")

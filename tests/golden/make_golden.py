@@ -146,6 +146,11 @@ def main():
         classes["harmonic"], img, mask, convolver="opencv", max_iters=10, term_thres=1e-300,
         term_check_iters=10 ** 9, update_step_size=0.2, relaxation=1.5)
     out["sweeps__harmonic_relax15__opencv__f64__10"] = res
+    # AMLE with 1-D convolutions (scipy.ndimage.convolve1d, symmetric border; amle_inpainter.py:26-37)
+    res, _, _, _, _, _ = run_reference(
+        classes["amle"], img, mask, convolver="opencv", max_iters=10, term_thres=1e-300,
+        term_check_iters=10 ** 9, update_step_size=0.01, convolve_in_1d=True)
+    out["sweeps__amle_1d__f64__10"] = res
     np.savez_compressed(os.path.join(HERE, "sweeps.npz"), **out)
 
     # ---------------------------------------------------------------- C. converged runs

@@ -124,6 +124,21 @@ def test_ccst_tension_end_points_and_relaxation(golden_sweeps):
     assert range_err(got, ref) <= TOL["f64"]
 
 
+def test_amle_convolve_in_1d_matches_reference(golden_sweeps):
+    """AMLE's scipy.ndimage.convolve1d branch: convolution orientation, symmetric borders."""
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__amle_1d__f64__10"]
+    inp = hmi.AMLEInpainter(update_step_size=0.01, convolve_in_1d=True, convolver="opencv", max_iters=10,
+                            term_thres=1e-300, term_check_iters=10 ** 9)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = inp.inpaint(img, mask)
+    assert np.array_equal(got[mask], ref[mask])
+    assert range_err(got, ref) <= TOL["f64"]
+
+
 def test_converged_runs_match_reference_through_public_api(golden_converged):
     """Inpainter(**options).inpaint(image, mask): same stop iteration, last diff, known cells, values."""
     mask = golden_converged["mask"]
@@ -346,3 +361,23 @@ def test_multigrid_matches_reference(golden_multigrid):
         assert range_err(got, ref) <= TOL[dt], (key, range_err(got, ref))
         assert np.allclose(caller, g[key + "_caller_after"], rtol=0, atol=1e-9 if dt == "f64" else 1e-3), key
         assert float(inp.term_thres) == pytest.approx(float(final_thres), rel=1e-6), key
+
+
+def test_converged_ccst_tracks_512_matches_oracle():
+    """A mid-size solve to convergence (BASELINE config 2 in small: CCST t=0.3, bathymetry, survey
+    tracks): same stop iteration and last diff as the oracle, filled cells within 1e-10."""
+    n = 512
+    img = synthetic.bathymetry(n, seed=7)
+    mask = synthetic.mask_tracks(n, 8, 16, 256)
+    img = synthetic.zero_unknown(img, mask)
+    opts = dict(update_step_size=0.01, tension=0.3, convolver="opencv", term_criteria="relative",
+                term_thres=1e-7, term_check_iters=100, max_iters=100000)
+    inp = hmi.CCSTInpainter(**opts)
+    got = inp.inpaint(img.copy(), mask)
+    ora = OracleInpainter("ccst", **opts)
+    ref = ora.inpaint(img.copy(), mask)
+    assert inp.converged_ and ora.converged
+    assert inp.iterations_ == ora.updates_done, (inp.iterations_, ora.updates_done)
+    assert inp.last_diff_ == pytest.approx(ora.last_diff, rel=1e-6)
+    assert np.array_equal(got[mask], img[mask])
+    assert range_err(got, ref) <= TOL["f64"], range_err(got, ref)

@@ -92,3 +92,12 @@ def test_converged_runs_match_reference(golden_converged):
         assert o.term_thres == pytest.approx(c["final_thres"], rel=1e-12), c  # absolute_percent mutation
         assert np.array_equal(got[mask], ref[mask]), c
         assert range_err(got, ref) <= (1e-11 if c["dtype"] == "f64" else 5e-6), c
+
+
+def test_amle_convolve_in_1d(golden_sweeps):
+    img = golden_sweeps["image__f64"].copy()
+    mask = golden_sweeps["mask"]
+    ref = golden_sweeps["sweeps__amle_1d__f64__10"]
+    o = OracleInpainter("amle", convolver="opencv", max_iters=10, term_thres=1e-300,
+                        term_check_iters=10 ** 9, update_step_size=0.01, convolve_in_1d=True)
+    assert range_err(o.inpaint(img, mask), ref) <= 1e-12
