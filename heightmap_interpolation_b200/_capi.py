@@ -55,6 +55,7 @@ SYMBOLS = {
     "hmi_set_problem_host": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz]),
     "hmi_set_problem_device": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
     "hmi_sweeps": (ctypes.c_int, [_vp, _i64, _vp]),
+    "hmi_sweeps_overlap": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "hmi_sweeps_norm": (ctypes.c_int, [_vp, _i64, _vp, ctypes.POINTER(HmiNorm)]),
     "hmi_run": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(HmiStatus)]),
     "hmi_get_result_host": (ctypes.c_int, [_vp, _vp, _sz]),

@@ -154,12 +154,13 @@ struct hmi_solver {
     long long launches = 0;
     bool has_problem = false;
     size_t grid_bytes = 0, mask_bytes = 0;
+    cudaEvent_t ev = nullptr;   // main -> side stream dependency of hmi_sweeps_overlap
 };
 
 namespace {
 
 template <typename T>
-int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st)
+int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip)
 {
     const hmi_params &p = s->p;
     const T *src = reinterpret_cast<const T *>(s->buf[s->cur]) + (long long)p.ghost_top * s->pitch;
@@ -223,14 +224,14 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
         return fail(HMI_ERR_STATE, "internal: %d blocks exceed the reduction scratch (%d)", nblocks,
                     s->max_blocks);
     s->launches += 1;
-    s->cur ^= 1;
+    if (flip) s->cur ^= 1;
     return HMI_OK;
 }
 
-int run_block(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st)
+int run_block(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip = true)
 {
-    return s->p.dtype == HMI_F64 ? run_block_t<double>(s, k, lo, hi, do_norm, st)
-                                 : run_block_t<float>(s, k, lo, hi, do_norm, st);
+    return s->p.dtype == HMI_F64 ? run_block_t<double>(s, k, lo, hi, do_norm, st, flip)
+                                 : run_block_t<float>(s, k, lo, hi, do_norm, st, flip);
 }
 
 // n sweeps as a sequence of temporal blocks.  On a slab with ghost rows the halos must be fresh
@@ -295,6 +296,7 @@ void destroy(hmi_solver *s)
     cached_free(s->p.device, s->mask, s->mask_bytes);
     cached_free(s->p.device, s->d_scratch, s->scratch_bytes);
     pinned_put(s->h_result);
+    if (s->ev) cudaEventDestroy(s->ev);
     delete s;
 }
 
@@ -519,6 +521,45 @@ int hmi_sweeps(hmi_solver *s, int64_t n, void *stream)
     if (!s) return fail(HMI_ERR_BAD_ARG, "null solver");
     CUDA_TRY(cudaSetDevice(s->p.device));
     return do_sweeps(s, n, false, (cudaStream_t)stream);
+}
+
+int hmi_sweeps_overlap(hmi_solver *s, int64_t n, void *main_stream, void *side_stream)
+{
+    if (!s) return fail(HMI_ERR_BAD_ARG, "null solver");
+    const hmi_params &p = s->p;
+    if (n < 1) return fail(HMI_ERR_BAD_ARG, "hmi_sweeps_overlap needs n >= 1");
+    CUDA_TRY(cudaSetDevice(p.device));
+    cudaStream_t ms = (cudaStream_t)main_stream, ss = (cudaStream_t)side_stream;
+    const int bt = p.ghost_top, bb = p.ghost_bottom;     // rows each neighbour needs from this slab
+    if ((bt == 0 && bb == 0) || p.rows - bt - bb < 8 || ss == ms)
+        return do_sweeps(s, n, false, ms);               // nothing to overlap with
+    long long k_last = n % s->tb == 0 ? s->tb : n % s->tb;
+    if (k_last > n) k_last = n;
+    const long long first = n - k_last;
+    if (n * s->radius > (bt > 0 ? bt : n * s->radius) || n * s->radius > (bb > 0 ? bb : n * s->radius))
+        return fail(HMI_ERR_BAD_ARG, "%lld sweeps need more ghost rows than the slab has", (long long)n);
+    // all blocks but the last: the shrinking trapezoid, on the main stream
+    long long done = 0;
+    while (done < first) {
+        long long k = first - done;
+        if (k > s->tb) k = s->tb;
+        const long long after = n - (done + k);
+        const int lo = bt > 0 ? (int)(-after * s->radius) : 0;
+        const int hi = p.rows + (bb > 0 ? (int)(after * s->radius) : 0);
+        const int rc = run_block(s, (int)k, lo, hi, false, ms);
+        if (rc != HMI_OK) return rc;
+        done += k;
+    }
+    // last block: the rows the neighbours are waiting for go first, on the side stream (the caller
+    // starts the halo exchange behind them); the interior follows on the main stream
+    if (!s->ev) CUDA_TRY(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(s->ev, ms));
+    CUDA_TRY(cudaStreamWaitEvent(ss, s->ev, 0));
+    int rc = HMI_OK;
+    if (bt > 0) rc = run_block(s, (int)k_last, 0, bt, false, ss, false);
+    if (rc == HMI_OK && bb > 0) rc = run_block(s, (int)k_last, p.rows - bb, p.rows, false, ss, false);
+    if (rc == HMI_OK) rc = run_block(s, (int)k_last, bt, p.rows - bb, false, ms, true);
+    return rc;
 }
 
 int hmi_sweeps_norm(hmi_solver *s, int64_t n, void *stream, hmi_norm *out)

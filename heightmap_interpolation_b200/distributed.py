@@ -52,6 +52,7 @@ class CudaSlabEngine:
         self.typestr = "<f8" if params.dtype == C.HMI_F64 else "<f4"
         self.elem = 8 if params.dtype == C.HMI_F64 else 4
         self._views = {}            # device pointer -> torch view (the solver ping-pongs two grids)
+        self._side = None           # side stream of the overlapped exchange
 
     def load(self, image, mask):
         self.solver.set_problem_host(image, mask)
@@ -71,6 +72,18 @@ class CudaSlabEngine:
 
     def sweeps(self, n):
         self.solver.sweeps(n)
+
+    def sweeps_overlap(self, n, exchange):
+        """n sweeps with the halo exchange of the *result* overlapped with the interior update: the
+        edge rows are produced first on a side stream, `exchange()` is queued behind them on that
+        stream, and the main stream only waits for it before the next block."""
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self.solver.sweeps_overlap(n, main.cuda_stream, self._side.cuda_stream)
+        with torch.cuda.stream(self._side):
+            exchange()
+        main.wait_stream(self._side)
 
     def sweeps_norm(self, n):
         return self.solver.sweeps_norm(n)
@@ -97,6 +110,8 @@ class SlabSolver:
         if world > 1 and self.exchange_every * radius > max(ghost_top, ghost_bottom):
             raise ValueError("exchange_every*radius exceeds the ghost depth")
         self.exchanges = 0
+        self.halo_fresh = True      # slabs are loaded with their neighbours' rows
+        self.overlap = hasattr(engine, "sweeps_overlap")
 
     # -- halo exchange: my first/last `g` interior rows -> the neighbour's ghost rows
     def exchange(self):
@@ -127,19 +142,32 @@ class SlabSolver:
             yield k
             n -= k
 
+    def _block(self, k):
+        """k <= exchange_every sweeps.  Halos are refreshed before the block if they are stale;
+        engines that can split their last launch refresh them again *after* it, overlapped with
+        the interior update, so the next block starts without waiting."""
+        if not self.halo_fresh:
+            self.exchange()
+        if self.overlap and self.world > 1:
+            self.engine.sweeps_overlap(k, self.exchange)
+            self.halo_fresh = True
+        else:
+            self.engine.sweeps(k)
+            self.halo_fresh = False
+
     def sweeps(self, n):
         for k in self._blocks(int(n)):
-            self.exchange()
-            self.engine.sweeps(k)
+            self._block(k)
 
     def sweeps_norm(self, n):
         n = int(n)
         blocks = list(self._blocks(n))
         for k in blocks[:-1]:
+            self._block(k)
+        if not self.halo_fresh:
             self.exchange()
-            self.engine.sweeps(k)
-        self.exchange()
         nm = self.engine.sweeps_norm(blocks[-1])
+        self.halo_fresh = False
         return self.allreduce_norm(nm)
 
     def allreduce_norm(self, nm):

@@ -107,6 +107,9 @@ class Solver:
     def sweeps(self, n, stream=0):
         C.check(self._lib.hmi_sweeps(self._h, int(n), stream))
 
+    def sweeps_overlap(self, n, main_stream, side_stream):
+        C.check(self._lib.hmi_sweeps_overlap(self._h, int(n), main_stream, side_stream))
+
     def sweeps_norm(self, n, stream=0):
         nm = C.HmiNorm()
         C.check(self._lib.hmi_sweeps_norm(self._h, int(n), stream, ctypes.byref(nm)))

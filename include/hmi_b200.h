@@ -129,6 +129,13 @@ int hmi_set_problem_device(hmi_solver *s, const void *image_dev, size_t image_pi
  * `stream`.  Replaces n iterations of the loop body fd_pde_inpainter.py:311-326 between checks. */
 int hmi_sweeps(hmi_solver *s, int64_t n, void *stream);
 
+/* Row slabs: n sweeps like hmi_sweeps, but the last temporal block is split so that the rows the
+ * neighbouring slabs need (the first ghost_top and last ghost_bottom interior rows) are produced
+ * first, on `side_stream`, and the interior rows on `main_stream`.  The caller starts the halo
+ * exchange on `side_stream` right after this call and makes `main_stream` wait for it before the
+ * next call, so the exchange overlaps the interior update.  Halos must be fresh on entry. */
+int hmi_sweeps_overlap(hmi_solver *s, int64_t n, void *main_stream, void *side_stream);
+
 /* n sweeps (n >= 1); the convergence sums between the last two iterates are reduced on the device,
  * fused into the last sweep, and returned (synchronises `stream`).
  * Replaces: the loop body + term_check() on a check iteration (fd_pde_inpainter.py:322-323, 368-379). */

@@ -258,7 +258,8 @@ def test_nan_never_converges_and_all_known_grid_is_identity():
                                                  ("tv", "generic", 3), ("amle", "generic", 2),
                                                  ("ccst", "generic", 2), ("tv", "stream", 3),
                                                  ("amle", "stream", 2)])
-def test_two_slabs_with_halo_exchange_equal_one_grid(method, kernel, block):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_slabs_with_halo_exchange_equal_one_grid(method, kernel, block, overlap):
     """Row-slab decomposition: two solvers with ghost rows, halos copied by the test between
     temporal blocks, must reproduce the single-grid result exactly (same kernels, same order)."""
     rows, cols = 160, 200
@@ -283,8 +284,15 @@ def test_two_slabs_with_halo_exchange_equal_one_grid(method, kernel, block):
             cur = np.vstack([top.get_result_host(), bot.get_result_host()])
             top.set_problem_host(cur[0:split + G], mask[0:split + G])
             bot.set_problem_host(cur[split - G:rows], mask[split - G:rows])
-        top.sweeps(block)
-        bot.sweeps(block)
+        if overlap:     # split last launch: edge rows on a side stream, interior on the main stream
+            import torch
+            side = torch.cuda.Stream()
+            top.sweeps_overlap(block, 0, side.cuda_stream)
+            bot.sweeps_overlap(block, 0, side.cuda_stream)
+            torch.cuda.synchronize()
+        else:
+            top.sweeps(block)
+            bot.sweeps(block)
     got = np.vstack([top.get_result_host(), bot.get_result_host()])
     top.close(); bot.close()
     assert np.array_equal(got, whole), float(np.abs(got - whole).max())
