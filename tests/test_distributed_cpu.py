@@ -85,5 +85,6 @@ def test_slab_solve_equals_single_grid(world, method, exchange_every):
     for r in res:
         assert r[4] == ref.updates_done and r[6] == ref.converged
         assert r[5] == pytest.approx(ref.last_diff, rel=1e-9)
-        assert r[7] >= ref.updates_done // max(exchange_every, 1)
+        # slabs are loaded with fresh halos, so the first block needs no exchange
+        assert r[7] >= (ref.updates_done - 1) // max(exchange_every, 1)
     assert np.array_equal(got, want)       # same arithmetic per cell: bit-exact
