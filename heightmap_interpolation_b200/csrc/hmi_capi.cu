@@ -12,6 +12,7 @@
 #include "hmi_common.cuh"
 #include "hmi_stream.cuh"
 #include "hmi_stream_nl.cuh"
+#include "hmi_init.cuh"
 
 namespace {
 
@@ -377,7 +378,6 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
                            p.border == HMI_BORDER_REFLECT101 && !(p.relaxation > 1.0);
     int tb = 1;
     bool use_stream = false;
-    bool use_nl = false;     // streaming kernel for TV / AMLE
     if (p.kernel == HMI_KERNEL_STREAM && !stream_ok && (p.method == HMI_HARMONIC || p.method == HMI_CCST)) {
         delete s;
         return fail(HMI_ERR_UNSUPPORTED, "streaming kernel needs reflect-101 borders and no over-relaxation");
@@ -452,8 +452,9 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
 {
     if (!s || !key) return fail(HMI_ERR_BAD_ARG, "null argument");
     if (!strcmp(key, "chunk_rows")) {
-        if (value < 0) return fail(HMI_ERR_BAD_ARG, "chunk_rows must be >= 0");
-        s->chunk_rows = value == 0 ? 0 : (value < 8 ? 8 : (int)value);
+        // 0 = wave-aware automatic choice, -1 = the older fixed-wave rule (A/B measurements)
+        if (value < -1) return fail(HMI_ERR_BAD_ARG, "chunk_rows must be >= -1");
+        s->chunk_rows = value <= 0 ? (int)value : (value < 8 ? 8 : (int)value);
         return HMI_OK;
     }
     if (!strcmp(key, "tma")) {
@@ -486,12 +487,20 @@ int hmi_set_problem_host(hmi_solver *s, const void *image, size_t image_pitch_by
         return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
     CUDA_TRY(cudaSetDevice(s->p.device));
     s->cur = 0;
-    CUDA_TRY(cudaMemcpy2D(s->buf[0], (size_t)s->pitch * s->elem, image, image_pitch_bytes, wbytes,
-                          s->phys_rows, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy2D(s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
-                          s->phys_rows, cudaMemcpyHostToDevice));
+    // dense rows on both sides: one linear copy each (the 2-D path costs ~1 ms more on a 128 MiB grid)
+    if (image_pitch_bytes == wbytes && (size_t)s->pitch * s->elem == wbytes)
+        CUDA_TRY(cudaMemcpyAsync(s->buf[0], image, wbytes * s->phys_rows, cudaMemcpyHostToDevice, nullptr));
+    else
+        CUDA_TRY(cudaMemcpy2DAsync(s->buf[0], (size_t)s->pitch * s->elem, image, image_pitch_bytes, wbytes,
+                                   s->phys_rows, cudaMemcpyHostToDevice, nullptr));
+    if (mask_pitch_bytes == (size_t)s->p.cols && (size_t)s->mpitch == (size_t)s->p.cols)
+        CUDA_TRY(cudaMemcpyAsync(s->mask, mask, (size_t)s->p.cols * s->phys_rows, cudaMemcpyHostToDevice, nullptr));
+    else
+        CUDA_TRY(cudaMemcpy2DAsync(s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
+                                   s->phys_rows, cudaMemcpyHostToDevice, nullptr));
     normalize_mask_kernel<<<592, 256>>>(s->mask, (size_t)s->phys_rows * s->mpitch);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(nullptr));    // the caller may reuse its host buffers on return
     s->has_problem = true;
     return HMI_OK;
 }
@@ -652,6 +661,67 @@ int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t 
     if (rc == HMI_OK) rc = hmi_run(s, nullptr, status);
     if (rc == HMI_OK) rc = hmi_get_result_host(s, out, (size_t)params->cols * elem);
     hmi_destroy(s);
+    return rc;
+}
+
+int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *mask, size_t mask_pitch_bytes,
+                          int32_t rows, int32_t cols, int32_t dtype, int32_t device)
+{
+    if (!image || !mask) return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (rows < 1 || cols < 1) return fail(HMI_ERR_BAD_ARG, "empty grid");
+    if (dtype != HMI_F32 && dtype != HMI_F64) return fail(HMI_ERR_BAD_ARG, "bad dtype");
+    const size_t elem = dtype == HMI_F64 ? 8 : 4;
+    const size_t wbytes = (size_t)cols * elem;
+    if (image_pitch_bytes < wbytes || mask_pitch_bytes < (size_t)cols)
+        return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(HMI_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(HMI_ERR_BAD_ARG, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    const long long pitch = round_up(cols, 32), mpitch = round_up(cols, 128);
+    const size_t gbytes = (size_t)rows * pitch * elem, mbytes = (size_t)rows * mpitch;
+    const size_t obytes = (size_t)rows * pitch * sizeof(int);
+    char *d_img = nullptr, *d_out = nullptr;
+    uint8_t *d_mask = nullptr;
+    int *d_off = nullptr, *d_status = nullptr;
+    int rc = HMI_OK, status = 0;
+    do {
+        if ((e = cached_malloc(device, (void **)&d_img, gbytes)) != cudaSuccess) break;
+        if ((e = cached_malloc(device, (void **)&d_out, gbytes)) != cudaSuccess) break;
+        if ((e = cached_malloc(device, (void **)&d_mask, mbytes)) != cudaSuccess) break;
+        if ((e = cached_malloc(device, (void **)&d_off, obytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&d_status, sizeof(int))) != cudaSuccess) break;
+        if ((e = cudaMemcpy2D(d_img, (size_t)pitch * elem, image, image_pitch_bytes, wbytes, rows,
+                              cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = cudaMemcpy2D(d_mask, (size_t)mpitch, mask, mask_pitch_bytes, (size_t)cols, rows,
+                              cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if (dtype == HMI_F64)
+            e = hmi::launch_init_nearest<double>((const double *)d_img, pitch, d_mask, mpitch, rows, cols, d_off,
+                                                 pitch, (double *)d_out, pitch, d_status, nullptr);
+        else
+            e = hmi::launch_init_nearest<float>((const float *)d_img, pitch, d_mask, mpitch, rows, cols, d_off,
+                                                pitch, (float *)d_out, pitch, d_status, nullptr);
+        if (e != cudaSuccess) break;
+        if ((e = cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if (status != 0) break;
+        e = cudaMemcpy2D(image, image_pitch_bytes, d_out, (size_t)pitch * elem, wbytes, rows, cudaMemcpyDeviceToHost);
+    } while (0);
+    if (e != cudaSuccess) {
+        rc = fail(HMI_ERR_CUDA, "nearest initialiser failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    } else if (status != 0) {
+        rc = fail(HMI_ERR_BAD_ARG, "the nearest initialiser needs at least one known cell");
+    }
+    cudaDeviceSynchronize();
+    cached_free(device, d_img, gbytes);
+    cached_free(device, d_out, gbytes);
+    cached_free(device, d_mask, mbytes);
+    cached_free(device, d_off, obytes);
+    if (d_status) cudaFree(d_status);
     return rc;
 }
 

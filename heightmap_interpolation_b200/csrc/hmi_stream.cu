@@ -24,6 +24,9 @@
 //   * The mask travels down the pipeline as a bit history (V bits per row per lane).
 //   * The convergence sums of the last fused sweep are accumulated per lane in fp64 and folded by
 //     warp shuffles + one block reduction + a fixed-order final fold (no extra pass over the grid).
+#include <cstdio>
+#include <cstdlib>
+
 #include "hmi_common.cuh"
 #include "hmi_stream.cuh"
 #include "hmi_stream_common.cuh"
@@ -38,6 +41,9 @@
 #ifndef HMI_STREAM_MINB
 #define HMI_STREAM_MINB 1   // __launch_bounds__ min CTAs per SM (1 = let ptxas choose)
 #endif
+#ifndef HMI_STREAM_SKEW
+#define HMI_STREAM_SKEW 1   // 1 = stage s+1 consumes stage s's row one step later (independent stages)
+#endif
 
 namespace hmi {
 
@@ -48,6 +54,14 @@ struct Geo {
     static constexpr int NCH = V / N;                   // 16-byte chunks per lane per row
     static constexpr int R = (METHOD == HMI_CCST) ? 2 : 1;
     static constexpr int H = K * R;                     // rows/columns of halo one launch consumes
+    // Skewed pipeline: the row a stage emits is consumed by the next stage in the *next* row step,
+    // so the K stages of one step have no data dependence on each other and their fp64 chains
+    // interleave (the unskewed loop could issue only every ~4th cycle per warp: each stage waited
+    // on the previous one).  Costs K-1 extra rows of latency per chunk, no registers.
+    // Measured (profiles/r02_tune_skew_ab.log): +9..13 % for CCST fp64, whose stage is two chained
+    // 5-point passes; -5..8 % for harmonic and for fp32, whose stages are too short to need it.
+    static constexpr int SK = (HMI_STREAM_SKEW && K > 1 && METHOD == HMI_CCST && sizeof(T) == 8) ? 1 : 0;
+    static constexpr int LAG = H + SK * (K - 1);        // step y emits sweep K of row y - LAG
     static constexpr int HV = ((H + V - 1) / V) * V;    // column halo rounded to whole lanes
     static constexpr int S = 32 * V - 2 * HV;           // columns a warp produces
     static constexpr int ROW_BYTES = 32 * V * (int)sizeof(T);
@@ -60,6 +74,9 @@ struct Geo {
     static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
     static_assert(S > 0, "temporal block too deep for this strip width");
 };
+
+template <bool SMALL> struct MaskHist { typedef unsigned long long type; };
+template <> struct MaskHist<true> { typedef unsigned type; };
 
 // Sum of the four neighbours of centre row b (rows above/below + lane halos)
 template <typename T, int V>
@@ -74,12 +91,12 @@ __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], cons
     }
 }
 
-// One warp streams its strip down one chunk of rows.  EDGE = the strip touches a grid edge (ghost
+// One warp streams its strip down one chunk of rows.  MODE 2 = the strip touches a grid edge (ghost
 // columns to mirror, rows to reflect or clamp); interior strips skip all of that and address
 // memory incrementally.  NORM = accumulate the convergence sums of the (single) sweep.
-template <typename T, int V, int K, int METHOD, int D, bool EDGE, bool NORM, bool TMA>
+template <typename T, int V, int K, int METHOD, int D, int MODE, bool NORM, bool TMA>
 __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsigned ring_s, const int lane,
-                                            const int win, const int chunk, double &n_d2, double &n_f2,
+                                            const int win, const int y0, const int y1, double &n_d2, double &n_f2,
                                             double &n_mx, double &n_nan)
 {
     typedef Geo<T, V, K, METHOD> G;
@@ -88,15 +105,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = TMA ? G::SLOT_T : G::SLOT;
     constexpr bool CC = (METHOD == HMI_CCST);
     constexpr unsigned VMASK = (1u << V) - 1u;
-    constexpr int LAG = H;                         // step y emits sweep K of row y - LAG
-    static_assert((H + 1) * V <= 64, "mask history does not fit 64 bits");
+    constexpr int SK = G::SK, LAG = G::LAG;
+    static_assert((LAG + 1) * V <= 64, "mask history does not fit 64 bits");
     static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
 
+    // MODE 0: interior (lean loop, incremental addressing); 1: only the rows need care (reflect-101 at
+    // the global top/bottom, clamping to the slab's memory) — same compute path as 0; 2: ghost
+    // columns as well (mirrored out of other lanes' ring slots).
+    constexpr bool REDGE = MODE >= 1;
+    constexpr bool CEDGE = MODE == 2 || (TMA && MODE >= 1);
     const int x0 = win * S - HV;
     const int col0 = x0 + lane * V;
-    const int y0 = a.row_lo + chunk * a.chunk_rows;
-    const int y1 = min(a.row_hi, y0 + a.chunk_rows);
     const int ybeg = y0 - H, yend = y1 + H;        // rows streamed: [ybeg, yend)
+    const int ystop = yend + SK * (K - 1);         // row steps: [ybeg, ystop) (the skew drains K-1 steps)
     const bool out_lane = (lane >= HV / V) && (lane < 32 - HV / V) && (col0 < a.cols);
     const T dt = a.dt;
     // CCST with folded coefficients: f' = f + c2*(sum of h's four neighbours) + c3*h,
@@ -109,8 +130,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     // path, which mirrors ghost columns out of other lanes' slots.
     const int mcol = col0 & ~3;
     const unsigned msh = (unsigned)(col0 & 3) * 8u;
-    const bool f_copies = EDGE ? ((col0 >= 0) && (col0 + V <= (int)a.pitch)) : true;
-    const bool m_copies = EDGE ? ((mcol >= 0) && (mcol + 4 <= (int)a.mpitch)) : true;
+    const bool f_copies = CEDGE ? ((col0 >= 0) && (col0 + V <= (int)a.pitch)) : true;
+    const bool m_copies = CEDGE ? ((mcol >= 0) && (mcol + 4 <= (int)a.mpitch)) : true;
 
     // Pipeline state.  Stage s keeps a 3-row window of its input field in F[s][0..2]; the row loop
     // is unrolled by 3 so the window rotates by renaming (no register moves): in phase PH the rows
@@ -119,7 +140,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     T F[K][3][V];
     T Hh[CC ? K : 1][3][V];                        // CCST: window of h = L f
     T FL[K], FR[K], HL[CC ? K : 1], HR[CC ? K : 1];
-    unsigned long long mhist = 0ull;
+    // mask history: V bits per row, newest row in the low bits; 32 bits when they suffice (the bit
+    // tests then compile to one LOP3 each instead of a 64-bit shift + compare)
+    typedef typename MaskHist<((LAG + 1) * V <= 32) && !TMA && V == 2>::type MH;   // (ptxas runs out of predicate registers on some V = 4 and TMA variants)
+    MH mhist = 0;
 #pragma unroll
     for (int s = 0; s < K; ++s) {
         FL[s] = FR[s] = T(0);
@@ -162,7 +186,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             if (ynext < yend && lane == 0) {
                 int ry = ynext;
                 int c_lo = x0, c_hi = x0 + 32 * V, m_lo = mx16, m_hi = ((x0 + 32 * V + 15) & ~15);
-                if (EDGE) {
+                if (REDGE) {
                     if (ry < 0 && a.top_border) ry = -ry;
                     else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
                     ry = max(a.read_lo, min(a.read_hi - 1, ry));
@@ -183,7 +207,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             if (ynext < yend) {
                 const T *prow = gnext;
                 const uint8_t *mrow = mnext;
-                if (EDGE) {                        // reflect-101 at global edges, clamp to memory
+                if (REDGE) {                       // reflect-101 at global edges, clamp to memory
                     int ry = ynext;
                     if (ry < 0 && a.top_border) ry = -ry;
                     else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
@@ -198,7 +222,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                 if (m_copies) cp_async4(ring_m + wofs, mrow);
             }
             cp_async_commit();
-            if (!EDGE) { gnext += a.pitch; mnext += a.mpitch; }
+            if (!REDGE) { gnext += a.pitch; mnext += a.mpitch; }
         }
         ++ynext;
         wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
@@ -215,10 +239,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         constexpr int PH = decltype(ph)::value;
         constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
         if (TMA) {
-            mbar_wait(bar_s + 8 * ridx, rphase);   // both bulk copies of row y have landed
-        } else {
+            if (y < yend) mbar_wait(bar_s + 8 * ridx, rphase);   // both bulk copies of row y have landed
+        } else {                                   // (no row is fetched for the drain steps of the skew)
             cp_async_wait<D - 2>();                // this lane's copies of row y have landed
-            if (EDGE) __syncwarp();                // ... and the other lanes' (for the mirrors)
+            if (CEDGE) __syncwarp();               // ... and the other lanes' (for the mirrors)
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -241,7 +265,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             if (V == 4) mb = (w * 0x08040201u) >> 24;
             else mb = ((((w >> sh) & 0xffffu) * 0x0201u) >> 8) & 3u;
         }
-        if (EDGE) {
+        if (CEDGE) {
             // Ghost columns take the value and mask of their mirror cell, which sits in this
             // strip's ring slot (copied by another lane).  Lanes outside the allocation copied
             // nothing and read stale bytes, so clamp the bit group first.
@@ -272,7 +296,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                 }
             }
         }
-        mhist = (mhist << V) | (unsigned long long)mb;
+        mhist = (MH)(mhist << V) | (MH)mb;
         rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
         if (TMA) {
             ridx = (ridx + 1 == D) ? 0u : ridx + 1;
@@ -282,11 +306,14 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         issue();                                   // refills the slot read one step ago
 
         T res[V];
+        // Skewed: stages run last to first, each reads its window and then the stage before it
+        // overwrites that window's oldest row (IU) with the row that becomes "newest" next step.
 #pragma unroll
-        for (int s = 0; s < K; ++s) {
+        for (int si = 0; si < K; ++si) {
+            const int s = SK ? K - 1 - si : si;
             const T(&rin)[V] = F[s][IN];           // newest row of this stage's input field
             T o[V];
-            const unsigned kb = (unsigned)(mhist >> ((R * s + R) * V)) & VMASK;
+            const unsigned kb = (unsigned)(mhist >> ((s * (R + SK) + R) * V)) & VMASK;
             T s4[V];
             sum4_row<T, V>(F[s][IU], F[s][IC], rin, FL[s], FR[s], s4);
             // halos of the newest row, for the next step; issued after the last use of the old
@@ -333,7 +360,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             }
             if (s < K - 1) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) F[s + 1][IN][v] = o[v];
+                for (int v = 0; v < V; ++v) F[s + 1][SK ? IU : IN][v] = o[v];
             } else {
 #pragma unroll
                 for (int v = 0; v < V; ++v) res[v] = o[v];
@@ -354,10 +381,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         dptr += a.pitch;
     };
 
-    for (int y = ybeg; y < yend; y += 3) {
+    for (int y = ybeg; y < ystop; y += 3) {
         step(Phase<0>(), y);
-        if (y + 1 < yend) step(Phase<1>(), y + 1);
-        if (y + 2 < yend) step(Phase<2>(), y + 2);
+        if (y + 1 < ystop) step(Phase<1>(), y + 1);
+        if (y + 2 < ystop) step(Phase<2>(), y + 2);
     }
     if (!TMA) cp_async_wait<0>();
 }
@@ -373,22 +400,41 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
     const int wib = threadIdx.x >> 5;
     const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * WARP_RING;
     const long long gw = (long long)blockIdx.x * WPB + wib;
-    const int win = (int)(gw % a.nwin);
-    const int chunk = (int)(gw / a.nwin);
     double n_d2 = 0.0, n_f2 = 0.0, n_mx = 0.0, n_nan = 0.0;
 
-    if (chunk < a.nchunks) {
+    // warp -> (strip, chunk).  The n_edge column-edge strips (first, last) run the slower general
+    // path, so they come first and in shorter chunks; the other strips share one chunk height.
+    int win, chunk, ch_rows;
+    bool valid;
+    const long long n_e = (long long)a.n_edge * a.nchunks_e;
+    if (gw < n_e) {
+        win = (int)(gw % a.n_edge) == 0 ? 0 : a.nwin - 1;
+        chunk = (int)(gw / a.n_edge);
+        ch_rows = a.chunk_rows_e;
+        valid = true;
+    } else {
+        const long long g = gw - n_e;
+        const int ni = a.nwin - a.n_edge;
+        valid = ni > 0 && g < (long long)ni * a.nchunks;
+        win = ni > 0 ? (a.n_edge ? 1 : 0) + (int)(g % ni) : 0;
+        chunk = ni > 0 ? (int)(g / ni) : 0;
+        ch_rows = a.chunk_rows;
+    }
+
+    if (valid) {
         const int x0 = win * G::S - G::HV;
-        const int y0 = a.row_lo + chunk * a.chunk_rows;
-        const int y1 = min(a.row_hi, y0 + a.chunk_rows);
+        const int y0 = a.row_lo + chunk * ch_rows;
+        const int y1 = min(a.row_hi, y0 + ch_rows);
         const int ybeg = y0 - G::H, yend = y1 + G::H;
         const bool col_edge = (x0 < 0) || (x0 + 32 * V > a.cols);
         const bool row_edge = (ybeg < 0 && a.top_border) || (yend > a.rows && a.bottom_border) ||
                               (ybeg < a.read_lo) || (yend > a.read_hi);
-        if (col_edge || row_edge)
-            stream_rows<T, V, K, METHOD, D, true, NORM, TMA>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+        if (col_edge)
+            stream_rows<T, V, K, METHOD, D, 2, NORM, TMA>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+        else if (row_edge)
+            stream_rows<T, V, K, METHOD, D, 1, NORM, TMA>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows<T, V, K, METHOD, D, false, NORM, TMA>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 0, NORM, TMA>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -405,27 +451,87 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
     StreamArgs<T> a = a0;
     a.nwin = (a.cols + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
-    if (a.chunk_rows <= 0) a.chunk_rows = stream_auto_chunk_rows(nrows, a.nwin, G::H);
-    a.nchunks = (nrows + a.chunk_rows - 1) / a.chunk_rows;
-    const long long warps = (long long)a.nwin * a.nchunks;
-    const int blocks = (int)((warps + WPB - 1) / WPB);
-    if (nblocks_out) *nblocks_out = blocks;
     auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM, TMA>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static int cta_slots = 0;         // per instantiation: CTAs resident on the whole GPU at once
+    if (cta_slots == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        cta_slots = stream_cta_slots((const void *)kern, WPB * 32, SMEM);
     }
+    a.n_edge = 0;
+    a.nchunks_e = 0;
+    a.chunk_rows_e = 0;
+    if (a.chunk_rows == 0) {
+        a.n_edge = a.nwin >= 2 ? 2 : 1;
+        stream_pick_chunks(nrows, a.nwin, a.n_edge, G::H + G::SK * (K - 1), WPB, cta_slots, &a.chunk_rows,
+                           &a.chunk_rows_e);
+        a.nchunks_e = (nrows + a.chunk_rows_e - 1) / a.chunk_rows_e;
+    } else if (a.chunk_rows < 0) {
+        a.chunk_rows = stream_auto_chunk_rows(nrows, a.nwin, G::H);
+    }
+    a.nchunks = (nrows + a.chunk_rows - 1) / a.chunk_rows;
+    const long long warps = (long long)a.n_edge * a.nchunks_e + (long long)(a.nwin - a.n_edge) * a.nchunks;
+    const int blocks = (int)((warps + WPB - 1) / WPB);
+    if (nblocks_out) *nblocks_out = blocks;
+    static int debug = -1;
+    if (debug < 0) debug = getenv("HMI_DEBUG") ? 1 : 0;
+    if (debug)
+        fprintf(stderr, "[hmi] stream T=%d V=%d K=%d method=%d norm=%d: rows=%d nwin=%d chunk=%d x%d edge=%d x%d "
+                        "blocks=%d slots=%d (%.2f waves)\n", (int)sizeof(T), V, K, METHOD, (int)NORM, nrows, a.nwin,
+                a.chunk_rows, a.nchunks, a.chunk_rows_e, a.nchunks_e, blocks, cta_slots, (double)blocks / cta_slots);
     kern<<<blocks, WPB * 32, SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
+int stream_cta_slots(const void *kernel, int threads, size_t smem)
+{
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    cudaGetLastError();
+    return sms * occ;
+}
+
+void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, int *chunk_rows,
+                        int *chunk_rows_edge)
+{
+    // Wave-aware chunk heights.  Every warp streams (chunk + 2*halo) rows plus a pipeline fill and
+    // the launch takes ceil(CTAs / resident CTAs) rounds of that; a fixed chunk height leaves the
+    // last round partly empty (4096^2, fp64 CCST: SMs idle for 22 % of the kernel,
+    // profiles/r01_ncu_full_ccst_f64_k3_summary.txt).  Pick the chunk count that minimises
+    // rounds * rows-per-warp.  The column-edge strips run the general code path (~1.7x the
+    // instructions per row), so they get chunks 1.7x shorter and are scheduled first; without that
+    // a single full wave is slower than three ragged ones (profiles/r02_tune_skew_ab.log).
+    const int fill = 8;
+    const double edge_cost = 1.7;
+    int lo = 4 * halo;
+    if (lo < 24) lo = 24;
+    if (lo > nrows) lo = nrows;
+    double best = 1e300;
+    int best_ch = nrows, best_che = nrows;
+    const int max_nch = nrows / lo > 0 ? nrows / lo : 1;
+    for (int nch = 1; nch <= max_nch; ++nch) {
+        const int ch = (nrows + nch - 1) / nch;
+        if (ch < lo) break;
+        const int n = (nrows + ch - 1) / ch;                      // chunks this height really gives
+        int che = (int)((ch + 2 * halo + fill) / edge_cost) - 2 * halo - fill;
+        if (che < 8) che = 8;
+        if (che > ch) che = ch;
+        const int ne = (nrows + che - 1) / che;
+        const long long warps = (long long)n_edge * ne + (long long)(nwin - n_edge) * n;
+        const long long ctas = (warps + wpb - 1) / wpb;
+        const long long rounds = (ctas + cta_slots - 1) / cta_slots;
+        const double cost = (double)rounds * (ch + 2 * halo + fill) * (1.0 + ch / 8192.0);
+        if (cost <= best) { best = cost; best_ch = ch; best_che = che; }
+    }
+    *chunk_rows = best_ch < 8 ? 8 : best_ch;
+    *chunk_rows_edge = best_che < 8 ? 8 : best_che;
+}
+
 int stream_auto_chunk_rows(int nrows, int nwin, int halo)
 {
-    // Measured on B200 (profiles/r01_tune*.log): short chunks keep the warps that run together in
-    // one band of rows (DRAM/L2 locality) and give small grids several waves; chunks shorter than
-    // ~10x the halo pay for the 2*halo redundant rows.  Aim at ~4 waves of 16 warps per SM, within
+    // Legacy rule (chunk_rows < 0), kept for A/B measurements: ~4 waves of 16 warps per SM, within
     // [max(64, 10*halo), 192] rows.
     const long long target_warps = 148LL * 16 * 4;
     long long ch = ((long long)nrows * nwin + target_warps - 1) / target_warps;

@@ -18,10 +18,11 @@ struct StreamArgs {
     int row_lo, row_hi;         // rows written by this launch [row_lo, row_hi)
     int read_lo, read_hi;       // rows that exist in memory [read_lo, read_hi) (ghosts included)
     int top_border, bottom_border;
-    int chunk_rows;             // rows per warp chunk; <= 0 = auto
+    int chunk_rows;             // rows per warp chunk; 0 = auto (wave-aware), < 0 = legacy auto rule
     int vec;                    // cells per lane (fp64: 2 or 4; 0 = default)
     int tma;                    // 1 = stage rows with TMA bulk copies + mbarriers instead of cp.async
     int nwin, nchunks;          // filled by the launcher
+    int n_edge, nchunks_e, chunk_rows_e;   // column-edge strips: how many (listed first), their chunking
     T dt, tension, one_minus_tension;
     int do_norm;
     double *partials;
@@ -35,7 +36,10 @@ cudaError_t launch_stream(int method, int k, const StreamArgs<T> &a, cudaStream_
 
 int stream_max_k(int method, int dtype);
 int stream_halo(int method, int k);                 // ghost rows/columns k fused sweeps consume
-int stream_auto_chunk_rows(int nrows, int nwin, int halo);
+int stream_auto_chunk_rows(int nrows, int nwin, int halo);      // legacy rule (chunk_rows < 0)
+int stream_cta_slots(const void *kernel, int threads, size_t smem);   // CTAs resident on the GPU at once
+void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, int *chunk_rows,
+                        int *chunk_rows_edge);                  // wave-aware (chunk_rows == 0)
 int stream_max_blocks(int method, int rows_total, int cols);
 
 }  // namespace hmi

@@ -21,6 +21,7 @@
 //     slow-path fp64 operations than the generic kernel, which evaluates the normalisation at the
 //     three cells a step touches.
 #include "hmi_stream_nl.cuh"
+#include "hmi_stream.cuh"
 #include "hmi_stream_common.cuh"
 
 namespace hmi {
@@ -320,18 +321,19 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     a.cbase = a.clo - (a.clo % V);
     a.nwin = (a.chi - a.cbase + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
+    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM>;
+    static int cta_slots = 0;
+    if (cta_slots == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return e;
+        cta_slots = stream_cta_slots((const void *)kern, WPB * 32, SMEM);
+    }
+    (void)cta_slots;    // the wave-aware picker of hmi_stream.cu measured slower here (one sweep per launch is HBM bound)
     a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
     a.nchunks = (nrows + a.chunk_rows - 1) / a.chunk_rows;
     const long long warps = (long long)a.nwin * a.nchunks;
     const int blocks = (int)((warps + WPB - 1) / WPB);
     if (nblocks_out) *nblocks_out = blocks;
-    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     kern<<<blocks, WPB * 32, SMEM, st>>>(a);
     return cudaGetLastError();
 }

@@ -182,19 +182,36 @@ class SlabSolver:
         return Norm(float(sums[0]), float(sums[1]), float(maxs[0]), float(maxs[1]))
 
 
+def slab_rows_needed(rows, world, rank, radius, exchange_every):
+    """Rows [a, b) of the global grid rank `rank` must hold (its slab plus ghost rows) and the
+    exchange depth actually used — what `inpaint_slab(..., first_row=a, global_rows=rows)` expects."""
+    bounds = slab_bounds(rows, world)
+    r0, r1 = bounds[rank]
+    min_rows = min(b - a for a, b in bounds)
+    E = max(1, min(int(exchange_every), (min_rows - 1) // radius if world > 1 else 10 ** 9))
+    ghost = radius * E if world > 1 else 0
+    return r0 - (ghost if rank > 0 else 0), r1 + (ghost if rank < world - 1 else 0), E
+
+
 def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=None,
-                 engine_factory=None, group=None):
+                 engine_factory=None, group=None, global_rows=None, first_row=0, post_hook=None):
     """Distributed `inpaint_grid`: every rank passes the same global `image`/`mask` (already
-    initialised, host arrays) or — to save host memory — any arrays whose rows [r0-ghost, r1+ghost)
-    are valid; returns this rank's interior rows and its (r0, r1).
+    initialised, host arrays), or — so that no process ever holds the whole grid — only the rows
+    [first_row, first_row + len(image)) of a grid of `global_rows` rows, which must cover this
+    rank's slab and ghost rows (`slab_rows_needed`); returns this rank's interior rows and its
+    (r0, r1).  With partial arrays the z-range of `absolute_percent` is all-reduced.
 
     The loop semantics (check cadence, stop rule, progress table on rank 0) are those of
     FDPDEInpainter._loop.  `engine_factory(params)` exists for the CPU tests (gloo + a CPU engine);
-    the product path always builds CudaSlabEngine.
+    the product path always builds CudaSlabEngine.  `post_hook(slab)` (benchmarks) runs after the solve
+    while the slab is still resident.
     """
     rank = dist.get_rank(group) if rank is None else rank
     world = dist.get_world_size(group) if world is None else world
     rows, cols = image.shape
+    partial = global_rows is not None
+    if partial:
+        rows = int(global_rows)
     radius = 2 if inpainter.METHOD == C.HMI_CCST else 1
     bounds = slab_bounds(rows, world)
     r0, r1 = bounds[rank]
@@ -206,14 +223,25 @@ def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=N
     gt = ghost if rank > 0 else 0
     gb = ghost if rank < world - 1 else 0
 
-    inpainter.set_term_criteria(image)   # every rank sees the same global z-range
     device = inpainter._device() if engine_factory is None else 0
+    if partial:
+        a, b = r0 - gt - first_row, r1 + gb - first_row
+        if a < 0 or b > image.shape[0]:
+            raise ValueError("rows [%d, %d) needed, the arrays hold [%d, %d)"
+                             % (r0 - gt, r1 + gb, first_row, first_row + image.shape[0]))
+        image, mask = image[a:b], mask[a:b]
+        _set_term_criteria_global(inpainter, image[gt:gt + (r1 - r0)], world, group,
+                                  torch.device("cuda", device) if engine_factory is None else torch.device("cpu"))
+        lo = 0
+    else:
+        inpainter.set_term_criteria(image)   # every rank sees the same global z-range
+        lo = r0 - gt
     params = inpainter._make_params(r1 - r0, cols, image.dtype, ghost_top=gt, ghost_bottom=gb,
                                     device=device)
     engine = (engine_factory or CudaSlabEngine)(params)
     try:
-        engine.load(np.ascontiguousarray(image[r0 - gt:r1 + gb]),
-                    np.ascontiguousarray(mask[r0 - gt:r1 + gb]))
+        engine.load(np.ascontiguousarray(image[lo:lo + gt + (r1 - r0) + gb]),
+                    np.ascontiguousarray(mask[lo:lo + gt + (r1 - r0) + gb]))
         slab = SlabSolver(engine, rank, world, radius, gt, gb, exchange_every, r1 - r0, group)
         quiet = inpainter.print_progress and rank != 0
         if quiet:
@@ -227,6 +255,34 @@ def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=N
         inpainter.exchanges_ = slab.exchanges
         if not conv and rank == 0:
             print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
-        return engine.result(), (r0, r1)
+        result = engine.result()
+        if post_hook is not None:
+            post_hook(slab)
+        return result, (r0, r1)
     finally:
         engine.close()
+
+
+class _RangeView:
+    """Stands in for the global grid in set_term_criteria(): only max() and min() are taken."""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def max(self, *a, **k):
+        return self.hi
+
+    def min(self, *a, **k):
+        return self.lo
+
+
+def _set_term_criteria_global(inpainter, interior, world, group, dev):
+    """set_term_criteria (fd_pde_inpainter.py:141-158) when no rank holds the whole grid: the
+    z-range of 'absolute_percent' is the all-reduced max/min of the slabs."""
+    if inpainter.term_criteria != "absolute_percent" or world == 1:
+        inpainter.set_term_criteria(interior)
+        return
+    t = torch.tensor([float(np.max(interior)), -float(np.min(interior))], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    t = t.cpu()
+    inpainter.set_term_criteria(_RangeView(interior.dtype.type(-float(t[1])), interior.dtype.type(float(t[0]))))

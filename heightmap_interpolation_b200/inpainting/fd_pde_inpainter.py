@@ -8,7 +8,7 @@ convergence norm — runs in hand-written CUDA kernels behind the C ABI of ``inc
 
 Extra keywords (ignored by the reference, which silently drops unknown keys):
 ``device`` (CUDA ordinal), ``kernel`` ("auto" | "generic" | "stream"), ``temporal_block`` (sweeps fused
-per launch, 0 = auto).  After a solve the object exposes ``iterations_``, ``last_diff_`` and
+per launch, 0 = auto), ``nearest_backend`` ("b200" | "scipy": who evaluates ``init_with="nearest"``).  After a solve the object exposes ``iterations_``, ``last_diff_`` and
 ``converged_`` (the reference only prints them).
 """
 import math
@@ -74,7 +74,8 @@ class FDPDEInpainter(ABC):
         self.map_term_criteria_str_to_int = {"relative": 0, "absolute": 1, "absolute_percent": 2}
         self.print_progress_table_row_str = "|{:>11d}|{:>17.10f}|"
         self.print_progress_last_table_row_str = "| CONVERGED |{:>17.10f}|"
-        self.initializer = Initializer(self.init_with)
+        self.initializer = Initializer(self.init_with, nearest_backend=kwargs.pop("nearest_backend", "b200"),
+                                       device=self.device)
 
         # results of the last solve
         self.iterations_ = None

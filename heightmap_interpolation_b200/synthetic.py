@@ -31,33 +31,44 @@ def gaussian_hill(n, dtype=np.float64):
     return out
 
 
-def bathymetry(n, seed=7, dtype=np.float64):
-    """-2500 + sum_o (1200/2^o) sin(2 pi 2^o x/C + phi_o) cos(2 pi 2^o y/R + psi_o), o = 0..5."""
+def bathymetry(n, seed=7, dtype=np.float64, row_range=None):
+    """-2500 + sum_o (1200/2^o) sin(2 pi 2^o x/C + phi_o) cos(2 pi 2^o y/R + psi_o), o = 0..5.
+    `row_range=(a, b)` returns only rows [a, b) of the grid (identical values), for row slabs."""
     rows, cols = _shape(n)
+    a, b = (0, rows) if row_range is None else (int(row_range[0]), int(row_range[1]))
     rng = np.random.default_rng(seed)
     phi = rng.uniform(0.0, 2.0 * np.pi, 6)
     psi = rng.uniform(0.0, 2.0 * np.pi, 6)
     x = np.arange(cols, dtype=np.float64)
     sx = [np.sin(2.0 * np.pi * (2 ** o) * x / cols + phi[o]) for o in range(6)]
-    out = np.empty((rows, cols), dtype=dtype)
-    for r0 in range(0, rows, _BLOCK):
-        y = np.arange(r0, min(rows, r0 + _BLOCK), dtype=np.float64)
+    out = np.empty((b - a, cols), dtype=dtype)
+    for r0 in range(a, b, _BLOCK):
+        y = np.arange(r0, min(b, r0 + _BLOCK), dtype=np.float64)
         acc = np.full((len(y), cols), -2500.0)
         for o in range(6):
             cy = np.cos(2.0 * np.pi * (2 ** o) * y / rows + psi[o])
             acc += (1200.0 / 2 ** o) * cy[:, None] * sx[o][None, :]
-        out[r0:r0 + len(y)] = acc.astype(dtype)
+        out[r0 - a:r0 - a + len(y)] = acc.astype(dtype)
     return out
 
 
-def mask_random(n, p, seed=0):
-    """Known where rng.random > p (so a fraction p of the cells is unknown)."""
+def mask_random(n, p, seed=0, row_range=None):
+    """Known where rng.random > p (so a fraction p of the cells is unknown).  `row_range=(a, b)`
+    returns only rows [a, b) of the same mask (the generator is advanced past the other blocks)."""
     rows, cols = _shape(n)
+    a, b = (0, rows) if row_range is None else (int(row_range[0]), int(row_range[1]))
     rng = np.random.default_rng(seed)
-    out = np.empty((rows, cols), dtype=bool)
+    out = np.empty((b - a, cols), dtype=bool)
     for r0 in range(0, rows, _BLOCK):
         nb = min(rows, r0 + _BLOCK) - r0
-        out[r0:r0 + nb] = rng.random((nb, cols)) > p
+        if r0 >= b:
+            break
+        if r0 + nb <= a:
+            rng.bit_generator.advance(nb * cols)       # one 64-bit draw per double
+            continue
+        blk = rng.random((nb, cols)) > p
+        lo, hi = max(a, r0), min(b, r0 + nb)
+        out[lo - a:hi - a] = blk[lo - r0:hi - r0]
     return out
 
 

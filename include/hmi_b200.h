@@ -168,6 +168,17 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes);
 int hmi_host_fill_unknown(void *image, const uint8_t *mask, int64_t n, int32_t dtype, double value);
 int hmi_host_known_mean(const void *image, const uint8_t *mask, int64_t n, int32_t dtype, double *mean);
 
+/* The 'nearest' initialiser on the device: every unknown cell (mask == 0) of the host array `image`
+ * takes the value of its Euclidean-nearest known cell, in place; known cells are untouched.  Host to
+ * device, an exact two-pass nearest-cell search and device to host all happen inside the call.
+ * Fails with HMI_ERR_BAD_ARG if there is no known cell.  Ties between equidistant known cells are
+ * broken towards the smaller column offset, then left, then up (SciPy's choice depends on its
+ * KD-tree's leaf order; the distance is always the same).
+ * Replaces: Initializer.initialize with init_with='nearest' (the CLI default, apps/apps_common.py:52),
+ * i.e. scipy.interpolate.griddata(method='nearest') over all known cells, inpainting/initializer.py:19-34. */
+int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *mask, size_t mask_pitch_bytes,
+                          int32_t rows, int32_t cols, int32_t dtype, int32_t device);
+
 /* Pre-fault a freshly allocated host buffer with several threads (the result array of inpaint()). */
 int hmi_host_prefault(void *buf, size_t bytes);
 
@@ -176,7 +187,7 @@ int hmi_host_prefault(void *buf, size_t bytes);
 int hmi_release_cache(void);
 
 /* Tuning knobs for tests and benchmarks: "chunk_rows" (rows per warp chunk of the streaming kernel,
- * 0 = auto) and "temporal_block" (sweeps fused per launch). */
+ * 0 = wave-aware automatic choice, -1 = the older fixed rule) and "temporal_block" (sweeps fused per launch). */
 int hmi_set_option(hmi_solver *s, const char *key, int64_t value);
 
 /* Introspection for tests and bench: sweeps fused per launch, kernels launched so far, and the

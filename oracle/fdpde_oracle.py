@@ -137,8 +137,10 @@ class OracleInpainter:
             image[~mask] = 0
         elif self.init_with == "mean":
             image[~mask] = np.mean(image[mask])
+        elif self.init_with == "nearest":
+            nearest_init(image, mask)
         else:
-            raise ValueError("oracle supports init_with zeros/mean only")
+            raise ValueError("oracle supports init_with zeros/mean/nearest only")
         return image
 
     def step_fun(self, f, work_mask=None):
@@ -181,6 +183,32 @@ class OracleInpainter:
     def inpaint(self, image, mask):
         image = self.initialize(image, mask)
         return self.inpaint_grid(image, mask)
+
+
+def nearest_init(image, mask, return_d2=False):
+    """initializer.py:19-34 with method='nearest' — scipy.interpolate.griddata over all known cells:
+    every unknown cell takes the value of its Euclidean-nearest known cell, in place.
+
+    Brute force in NumPy (small grids only).  SciPy's cKDTree returns *a* nearest point; which one
+    among equidistant points depends on its leaf order, so the restatement fixes a rule (and the
+    CUDA path follows the same one): smallest distance, then smallest |column offset|, then the
+    left column, then the upper row.  Pinned against the reference by tests/test_oracle_golden.py:
+    identical wherever the nearest cell is unique, same distance elsewhere."""
+    mask = np.asarray(mask, dtype=bool)
+    ky, kx = np.nonzero(mask)
+    if ky.size == 0:
+        raise ValueError("the nearest initialiser needs at least one known cell")
+    vals = image[mask]
+    d2 = np.zeros(image.shape, dtype=np.int64)
+    uy, ux = np.nonzero(~mask)
+    for i, j in zip(uy, ux):
+        dj = kx - j
+        dd = (ky - i) ** 2 + dj ** 2
+        # lexicographic key: distance, |dj|, left before right, upper before lower
+        key = np.lexsort((ky, dj, np.abs(dj), dd))[0]
+        image[i, j] = vals[key]
+        d2[i, j] = dd[key]
+    return (image, d2) if return_d2 else image
 
 
 def dilate3x3(unknown):

@@ -32,3 +32,8 @@ def golden_converged():
 @pytest.fixture(scope="session")
 def golden_multigrid():
     return np.load(os.path.join(GOLDEN, "multigrid.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_nearest():
+    return np.load(os.path.join(GOLDEN, "nearest.npz"))

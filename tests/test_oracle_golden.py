@@ -101,3 +101,35 @@ def test_amle_convolve_in_1d(golden_sweeps):
     o = OracleInpainter("amle", convolver="opencv", max_iters=10, term_thres=1e-300,
                         term_check_iters=10 ** 9, update_step_size=0.01, convolve_in_1d=True)
     assert range_err(o.inpaint(img, mask), ref) <= 1e-12
+
+
+def test_nearest_initialiser_matches_reference(golden_nearest):
+    """Initializer 'nearest' (initializer.py:19-34, scipy griddata): the restatement returns the
+    reference's value wherever the nearest known cell is unique, and a known cell at exactly the
+    reference's (minimal) distance elsewhere — SciPy's choice among equidistant cells is an
+    artefact of its KD-tree leaf order."""
+    from oracle.fdpde_oracle import nearest_init
+    g = golden_nearest
+    for row in g["meta"]:
+        key = str(row).split("|")[0]
+        img, mask = g[key + "_image"].copy(), g[key + "_mask"]
+        got, d2 = nearest_init(img, mask, return_d2=True)
+        ref, uniq = g[key + "_init"], g[key + "_unique"]
+        assert got is img                                   # in place, like the reference
+        assert np.array_equal(got[mask], ref[mask])
+        assert np.array_equal(d2, g[key + "_d2"]), key
+        assert np.array_equal(got[uniq], ref[uniq]), key
+        assert int((~uniq).sum()) > 0                       # the fixture does exercise ties
+
+
+def test_solve_from_reference_nearest_initialisation(golden_nearest):
+    """From the reference's own nearest initialisation the oracle reproduces the reference solve
+    (CLI-style options: absolute_percent, opencv) update for update."""
+    g = golden_nearest
+    upd, diff, term, final_thres = str(g["nn00_solve_meta"][0]).split("|")
+    o = OracleInpainter("harmonic", update_step_size=0.2, term_criteria="absolute_percent", term_thres=1e-6,
+                        term_check_iters=10, max_iters=100000, convolver="opencv")
+    got = o.inpaint_grid(g["nn00_init"].copy(), g["nn00_mask"])
+    assert (o.updates_done, o.converged) == (int(upd), bool(int(term)))
+    assert o.term_thres == pytest.approx(float(final_thres), rel=1e-12)
+    assert range_err(got, g["nn00_solve"]) <= 1e-12

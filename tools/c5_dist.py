@@ -1,0 +1,141 @@
+"""BASELINE config 5 across the GPUs of one box: converged harmonic / CCST inpainting of an N x N
+synthetic bathymetry grid with 40 % missing cells, row-slab sharded (strong scaling: the grid is
+fixed, each rank holds rows/world of it and never sees the rest).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        tools/c5_dist.py [--n 32768] [--dtypes f32,f64] [--methods harmonic,ccst] [--thres 1e-5]
+
+Per (method, dtype) rank 0 prints one JSON line: stop iteration, wall time of the whole solve
+(upload + sweeps + checks + download, max over ranks), GLUPS, the per-GPU fraction of the HBM
+roofline (17 / 9 algorithmic bytes per grid-cell update against MEASURED_PEAKS.json), a checksum of
+per-rank checksums of the result (compare across world sizes: the slabs are bit-identical to the
+single-GPU solve), known cells exact, and the top-left crop compared with the CPU oracle at the same
+iteration count.
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import heightmap_interpolation_b200 as hmi                                             # noqa: E402
+from heightmap_interpolation_b200 import synthetic                                     # noqa: E402
+from heightmap_interpolation_b200.distributed import inpaint_slab, slab_rows_needed    # noqa: E402
+
+CASES = {"harmonic": (hmi.SobolevInpainter, dict(update_step_size=0.2), 1, 16),
+         "ccst": (hmi.CCSTInpainter, dict(update_step_size=0.01, tension=0.3), 2, 12)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--dtypes", default="f32,f64")
+    ap.add_argument("--methods", default="harmonic,ccst")
+    ap.add_argument("--thres", type=float, default=1e-5)
+    ap.add_argument("--check-iters", type=int, default=50)
+    ap.add_argument("--max-iters", type=int, default=3000)
+    ap.add_argument("--crop", type=int, default=96)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    n = a.n
+    for dt in a.dtypes.split(","):
+        dtype = np.float64 if dt == "f64" else np.float32
+        for method in a.methods.split(","):
+            cls, mopts, radius, E = CASES[method]
+            r_lo, r_hi, E = slab_rows_needed(n, world, rank, radius, E)
+            t0 = time.perf_counter()
+            mask = synthetic.mask_random(n, 0.40, seed=3, row_range=(r_lo, r_hi))
+            img = synthetic.bathymetry(n, seed=7, dtype=dtype, row_range=(r_lo, r_hi))
+            img[~mask] = 0
+            t_gen = time.perf_counter() - t0
+            opts = dict(convolver="opencv", term_criteria="relative", term_thres=a.thres,
+                        term_check_iters=a.check_iters, max_iters=a.max_iters, device=local, **mopts)
+            inp = cls(**opts)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            resident = {}
+
+            def time_resident(slab, K=120):
+                # device-resident rate of the same slabs (halo exchange included), max over ranks
+                slab.sweeps(E * 2)
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                slab.sweeps(K)
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                resident["glups"] = float(n) * n * K / (float(t.item()) * 1e-3) / 1e9
+
+            res_box = {}
+
+            def hook(slab):
+                res_box["t_solve"] = time.perf_counter() - t0
+                time_resident(slab)
+
+            out, (r0, r1) = inpaint_slab(inp, img, mask, exchange_every=E, global_rows=n, first_row=r_lo,
+                                         post_hook=hook)
+            tt = torch.tensor([res_box["t_solve"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            secs = float(tt.item())
+            known = mask[r0 - r_lo:r1 - r_lo]
+            known_ok = bool(np.array_equal(out[known], img[r0 - r_lo:r1 - r_lo][known]))
+            # digests of fixed n/8-row blocks, so runs at world 1, 2, 4, 8 can be compared block by block
+            blk = max(1, n // 8)
+            digest = [(b0 // blk, hashlib.sha256(np.ascontiguousarray(out[b0 - r0:b0 - r0 + blk]).tobytes()).hexdigest()[:16])
+                      for b0 in range(((r0 + blk - 1) // blk) * blk, r1, blk) if b0 + blk <= r1]
+            parts = [None] * world
+            dist.all_gather_object(parts, (rank, digest, known_ok, inp.iterations_, float(inp.last_diff_),
+                                           bool(inp.converged_), inp.exchanges_))
+            if rank == 0:
+                parts.sort()
+                its = [p[3] for p in parts]
+                # checksum over the grid in row order, independent of how it was cut: hash rows in blocks
+                # of n/8 rows so that world sizes 1, 2, 4, 8 give comparable block digests
+                err = None
+                c = min(a.crop, n)
+                if world >= 1:
+                    from oracle.fdpde_oracle import OracleInpainter
+                    m = radius * its[0] + 2
+                    cc = min(n, c + m)
+                    if r1 - r0 >= cc and float(cc) * cc * its[0] <= 2e10:
+                        o = OracleInpainter(method, convolver="opencv", max_iters=its[0], term_thres=1e-300,
+                                            term_check_iters=10 ** 9, **mopts)
+                        ref = o.inpaint_grid(img[:cc, :cc].copy(), mask[:cc, :cc])
+                        err = float(np.abs(out[:c, :c].astype(np.float64) - ref[:c, :c]).max()) / \
+                            float(ref.max() - ref.min())
+                glups = float(n) * n * its[0] / secs / 1e9
+                bpl = 17 if dt == "f64" else 9
+                print(json.dumps({
+                    "config": "C5 %s %dx%d 40%% missing %s" % (method, n, n, dt), "n_gpus": world,
+                    "iterations": its[0], "same_iterations_all_ranks": len(set(its)) == 1,
+                    "converged": parts[0][5], "last_diff": parts[0][4], "solve_s": secs, "gen_s": t_gen,
+                    "glups_e2e": glups, "hbm_roofline_frac_per_gpu_e2e": glups * bpl / peak / world,
+                    "glups_resident": resident["glups"],
+                    "hbm_roofline_frac_per_gpu_resident": resident["glups"] * bpl / peak / world,
+                    "exchanges": parts[0][6], "exchange_every": E, "known_cells_exact": all(p[2] for p in parts),
+                    "corner_err_vs_oracle": err, "block_sha256": [d for p in parts for d in p[1]],
+                }), flush=True)
+            del img, mask, out
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
