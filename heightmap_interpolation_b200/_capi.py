@@ -62,12 +62,16 @@ SYMBOLS = {
     "hmi_get_result_device": (ctypes.c_int, [_vp, _vp, _sz, _vp]),
     "hmi_inpaint_host": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _vp, _vp,
                                         ctypes.POINTER(HmiStatus)]),
+    "hmi_inpaint_host_fill": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _vp, ctypes.c_double, _vp,
+                                             ctypes.POINTER(HmiStatus)]),
     "hmi_current_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_mask_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_host_fill_unknown": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, ctypes.c_double]),
     "hmi_host_known_mean": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
     "hmi_init_nearest_host": (ctypes.c_int, [_vp, _sz, _vp, _sz, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.c_int32]),
+    "hmi_host_known_minmax": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
+                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "hmi_host_prefault": (ctypes.c_int, [_vp, _sz]),
     "hmi_release_cache": (ctypes.c_int, []),
     "hmi_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64]),

@@ -127,6 +127,16 @@ __global__ void normalize_mask_kernel(uint8_t *m, size_t n)
     }
 }
 
+// Fused 'zeros' / 'mean' initialiser: unknown cells of the uploaded grid take `value`.
+template <typename T>
+__global__ void fill_unknown_kernel(T *f, long long pitch, const uint8_t *m, long long mpitch, int rows, int cols, T value)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    for (int i = blockIdx.y; i < rows; i += gridDim.y)
+        if (!m[(long long)i * mpitch + j]) f[(long long)i * pitch + j] = value;
+}
+
 }  // namespace
 
 struct hmi_solver {
@@ -384,8 +394,9 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     }
     if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
         const int maxk = hmi::stream_max_k(p.method, p.dtype);
-        tb = p.temporal_block > 0 ? p.temporal_block
-                                  : (p.method == HMI_CCST ? (p.dtype == HMI_F64 ? 3 : 4) : 6);
+        // measured (profiles/r02_tune_*): CCST 3 in both precisions (fp32: 3 = 4 at 16384^2, 3 % ahead
+        // at 4096^2), harmonic 6
+        tb = p.temporal_block > 0 ? p.temporal_block : (p.method == HMI_CCST ? 3 : 6);
         if (tb > maxk) tb = maxk;
         // the mirrored ghost loads need the mirror cell to exist: shrink the block on small grids
         const int min_dim = p.cols < p.rows ? p.cols : p.rows;
@@ -631,8 +642,11 @@ int hmi_get_result_host(hmi_solver *s, void *out, size_t out_pitch_bytes)
     CUDA_TRY(cudaSetDevice(s->p.device));
     CUDA_TRY(cudaDeviceSynchronize());
     const char *src = s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
-    CUDA_TRY(cudaMemcpy2D(out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows,
-                          cudaMemcpyDeviceToHost));
+    if (out_pitch_bytes == wbytes && (size_t)s->pitch * s->elem == wbytes)
+        CUDA_TRY(cudaMemcpy(out, src, wbytes * s->p.rows, cudaMemcpyDeviceToHost));
+    else
+        CUDA_TRY(cudaMemcpy2D(out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows,
+                              cudaMemcpyDeviceToHost));
     return HMI_OK;
 }
 
@@ -649,8 +663,8 @@ int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, 
     return HMI_OK;
 }
 
-int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
-                     hmi_status *status)
+static int inpaint_host_impl(const hmi_params *params, const void *image, const uint8_t *mask, bool fill,
+                             double fill_value, void *out, hmi_status *status)
 {
     if (!params || !image || !mask || !out || !status) return fail(HMI_ERR_BAD_ARG, "null argument");
     hmi_solver *s = nullptr;
@@ -658,10 +672,33 @@ int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t 
     if (rc != HMI_OK) return rc;
     const size_t elem = params->dtype == HMI_F64 ? 8 : 4;
     rc = hmi_set_problem_host(s, image, (size_t)params->cols * elem, mask, (size_t)params->cols);
+    if (rc == HMI_OK && fill) {
+        const dim3 grid((params->cols + 255) / 256, s->phys_rows < 1024 ? s->phys_rows : 1024);
+        if (params->dtype == HMI_F64)
+            fill_unknown_kernel<double><<<grid, 256>>>((double *)s->buf[0], s->pitch, s->mask, s->mpitch, s->phys_rows,
+                                                       params->cols, fill_value);
+        else
+            fill_unknown_kernel<float><<<grid, 256>>>((float *)s->buf[0], s->pitch, s->mask, s->mpitch, s->phys_rows,
+                                                      params->cols, (float)fill_value);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(HMI_ERR_CUDA, "fill kernel launch failed: %s", cudaGetErrorString(e));
+    }
     if (rc == HMI_OK) rc = hmi_run(s, nullptr, status);
     if (rc == HMI_OK) rc = hmi_get_result_host(s, out, (size_t)params->cols * elem);
     hmi_destroy(s);
     return rc;
+}
+
+int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
+                     hmi_status *status)
+{
+    return inpaint_host_impl(params, image, mask, false, 0.0, out, status);
+}
+
+int hmi_inpaint_host_fill(const hmi_params *params, const void *image, const uint8_t *mask, double fill_value,
+                          void *out, hmi_status *status)
+{
+    return inpaint_host_impl(params, image, mask, true, fill_value, out, status);
 }
 
 int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *mask, size_t mask_pitch_bytes,

@@ -71,9 +71,68 @@ double known_mean(const T *img, const uint8_t *mask, int64_t n)
     return c ? s / (double)c : std::nan("");
 }
 
+// min / max over the known cells, NaN-propagating like np.max / np.min
+template <typename T>
+void minmax_range(const T *__restrict__ img, const uint8_t *__restrict__ mask, int64_t a, int64_t b,
+                  double *mn, double *mx, int64_t *cnt, int *has_nan)
+{
+    double lo = INFINITY, hi = -INFINITY;
+    int64_t c = 0;
+    int nanf = 0;
+    for (int64_t i = a; i < b; ++i) {
+        if (!mask[i]) continue;
+        const double v = (double)img[i];
+        if (v != v) nanf = 1;
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+        ++c;
+    }
+    *mn = lo; *mx = hi; *cnt = c; *has_nan = nanf;
+}
+
+template <typename T>
+int64_t known_minmax(const T *img, const uint8_t *mask, int64_t n, double *mn, double *mx)
+{
+    const int nt = num_threads(n);
+    const int64_t per = (n + nt - 1) / nt;
+    std::vector<double> los(nt, INFINITY), his(nt, -INFINITY);
+    std::vector<int64_t> cnts(nt, 0);
+    std::vector<int> nans(nt, 0);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) {
+        const int64_t a = t * per, b = (a + per < n) ? a + per : n;
+        if (a < b) th.emplace_back(minmax_range<T>, img, mask, a, b, &los[t], &his[t], &cnts[t], &nans[t]);
+    }
+    minmax_range<T>(img, mask, 0, per < n ? per : n, &los[0], &his[0], &cnts[0], &nans[0]);
+    for (auto &x : th) x.join();
+    double lo = INFINITY, hi = -INFINITY;
+    int64_t c = 0;
+    int nanf = 0;
+    for (int t = 0; t < nt; ++t) {
+        lo = los[t] < lo ? los[t] : lo;
+        hi = his[t] > hi ? his[t] : hi;
+        c += cnts[t];
+        nanf |= nans[t];
+    }
+    if (nanf) lo = hi = std::nan("");
+    *mn = lo;
+    *mx = hi;
+    return c;
+}
+
 }  // namespace
 
 extern "C" {
+
+int hmi_host_known_minmax(const void *image, const uint8_t *mask, int64_t n, int32_t dtype, double *min_out,
+                          double *max_out, int64_t *known_out)
+{
+    if (!image || !mask || !min_out || !max_out || !known_out || n < 0) return HMI_ERR_BAD_ARG;
+    if (dtype == HMI_F64) *known_out = known_minmax<double>((const double *)image, mask, n, min_out, max_out);
+    else if (dtype == HMI_F32) *known_out = known_minmax<float>((const float *)image, mask, n, min_out, max_out);
+    else return HMI_ERR_BAD_ARG;
+    return HMI_OK;
+}
 
 int hmi_host_fill_unknown(void *image, const uint8_t *mask, int64_t n, int32_t dtype, double value)
 {

@@ -20,6 +20,9 @@
 //     two divides: within a few ulp, far inside the 1e-10 / 1e-5 parity bars, and 3x fewer
 //     slow-path fp64 operations than the generic kernel, which evaluates the normalisation at the
 //     three cells a step touches.
+#include <cstdio>
+#include <cstdlib>
+
 #include "hmi_stream_nl.cuh"
 #include "hmi_stream.cuh"
 #include "hmi_stream_common.cuh"
@@ -38,27 +41,46 @@ struct GeoNL {
     static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
 };
 
-__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+// fp32: the bare hardware approximation (MUFU.RSQ, 2 ulp) — rsqrtf() wraps it in a denormal-input
+// rescaling that a sum of squares plus a positive constant never needs.
+__device__ __forceinline__ float rsqrt_t(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// fp64: the hardware seed (MUFU.RSQ64H, ~2^-21) and one cubic refinement step, without the special-case call
+// CUDA's rsqrt() carries: the argument is a sum of squares plus a positive constant, always normal.
+__device__ __forceinline__ double rsqrt_t(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // one cubically convergent step: e = 1 - x y^2 (|e| < 2^-20), y <- y + y e (1/2 + 3/8 e); error ~ e^3
+    const double e = fma(-x, y * y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
 
-// One warp, one strip, one chunk of rows, in canonical coordinates (see header).
-template <typename T, int V, int METHOD, int SGN, int D, bool EDGE, bool NORM>
+// One warp, one strip, rows [y0, y1) of it, in canonical coordinates (see header).
+// MODE 0: interior (lean loop); 1: only the rows need care (reflect-101 at the global top/bottom,
+// clamping to the slab's memory, the "upper neighbour of row 0" rule); 2: ghost columns as well.
+// The row loop is unrolled by three so that the windows of f rows, lane halos and intermediate rows
+// rotate by register renaming: slot(row) = row mod 3.
+template <typename T, int V, int METHOD, int SGN, int D, int MODE, bool NORM>
 __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const unsigned ring_s, const int lane,
-                                               const int win, const int chunk, double &n_d2, double &n_f2,
-                                               double &n_mx, double &n_nan)
+                                               const int win, const int y0, const int y1, double &n_d2,
+                                               double &n_f2, double &n_mx, double &n_nan)
 {
     typedef GeoNL<T, V> G;
     typedef typename Chunk16<T>::type C16;
     constexpr int N = G::N, NCH = G::NCH, HV = G::HV, S = G::S, ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT;
     constexpr bool TV = (METHOD == HMI_TV);
+    constexpr bool REDGE = MODE >= 1, CEDGE = MODE == 2;
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int LAG = 2;                             // step y emits row y-2
 
     const int x0 = a.cbase + win * S - HV;             // canonical column of lane 0, cell 0
     const int col0 = x0 + lane * V;                    // canonical column of this lane's cell 0
     const int acol = SGN > 0 ? col0 : (int)a.pitch - col0 - V;   // actual column of the lane's chunk
-    const int y0 = a.row_lo + chunk * a.chunk_rows;    // canonical rows [y0, y1) are emitted
-    const int y1 = min(a.row_hi, y0 + a.chunk_rows);
     const int ybeg = y0 - 1, yend = y1 + 1;            // canonical rows fetched: [ybeg, yend)
     const int ystop = y1 + LAG;                        // steps: [ybeg, ystop)
     const bool out_lane = (lane >= 1) && (lane < 31) && (col0 < a.chi) && (col0 + V > a.clo);
@@ -67,8 +89,8 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 
     const int mcol = acol & ~3;
     const unsigned msh = (unsigned)(acol & 3) * 8u;
-    const bool f_copies = EDGE ? ((acol >= 0) && (acol + V <= (int)a.pitch)) : true;
-    const bool m_copies = EDGE ? ((mcol >= 0) && (mcol + 4 <= (int)a.mpitch)) : true;
+    const bool f_copies = CEDGE ? ((acol >= 0) && (acol + V <= (int)a.pitch)) : true;
+    const bool m_copies = CEDGE ? ((mcol >= 0) && (mcol + 4 <= (int)a.mpitch)) : true;
 
     const unsigned ring_f = ring_s + lane * 16;
     const unsigned ring_m = ring_s + ROW_BYTES + lane * 4;
@@ -87,7 +109,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
         if (ynext < yend) {
             const T *prow = gnext;
             const uint8_t *mrow = mnext;
-            if (EDGE) {                                // reflect-101 at the global edges, clamp to memory
+            if (REDGE) {                               // reflect-101 at the global edges, clamp to memory
                 int ry = ynext;
                 if (ry < 0 && a.top_border) ry = -ry;
                 else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
@@ -103,26 +125,37 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
         }
         cp_async_commit();
         ++ynext;
-        if (!EDGE) { gnext += rstep; mnext += mstep; }
+        if (!REDGE) { gnext += rstep; mnext += mstep; }
         wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
     };
 
 #pragma unroll
     for (int u = 0; u < D - 1; ++u) issue();
 
-    // f rows y-3, y-2, y-1 with the lane halos of rows y-2 and y-1; intermediates of rows y-2, y-3
-    T fA[V], fB[V], fC[V], L1 = T(0), R1 = T(0), L2 = T(0), R2 = T(0);
-    T P2[V], Q2[V], P3[V], Q3[V];
+    // slot(row) = row mod 3:  f rows y-2, y-1, y (and y-3 until row y lands in its slot), their lane
+    // halos, and the intermediate rows y-3, y-2, y-1 (n = g/|g| for TV, ux/uy for AMLE)
+    T F[3][V], P[3][V], Q[3][V], HL[3], HR[3];
 #pragma unroll
-    for (int v = 0; v < V; ++v) fA[v] = fB[v] = fC[v] = P2[v] = Q2[v] = P3[v] = Q3[v] = T(0);
+    for (int q = 0; q < 3; ++q) {
+        HL[q] = HR[q] = T(0);
+#pragma unroll
+        for (int v = 0; v < V; ++v) F[q][v] = P[q][v] = Q[q][v] = T(0);
+    }
     unsigned mhist = 0u;
     unsigned rofs = 0;
     T *dptr = a.dst + (long long)arow(ybeg - LAG) * a.pitch + acol;
 
-    for (int y = ybeg; y < ystop; ++y) {
+    auto step = [&](auto ph, const int y) {
+        constexpr int PH = decltype(ph)::value;
+        constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;   // rows y-2, y-1, y (and y-3)
+        // AMLE: v0 = f[r+1] - f[r-1] of the row emitted below, r = y-2; row y-3 still sits in slot IN
+        T v0[V];
+        if (!TV) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) v0[v] = F[IC][v] - F[IN][v];
+        }
         cp_async_wait<D - 2>();
-        if (EDGE) __syncwarp();
-        T cur[V];
+        if (CEDGE) __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             T e[N];
@@ -130,7 +163,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 #pragma unroll
             for (int q = 0; q < N; ++q) {
                 const int act = c * N + q;             // actual element -> canonical cell
-                cur[SGN > 0 ? act : V - 1 - act] = e[q];
+                F[IN][SGN > 0 ? act : V - 1 - act] = e[q];
             }
         }
         unsigned mb;                                   // canonical cell v -> bit V-1-v
@@ -139,7 +172,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
             if (V == 4) mb = (w * (SGN > 0 ? 0x08040201u : 0x01020408u)) >> 24;
             else mb = ((((w >> msh) & 0xffffu) * (SGN > 0 ? 0x0201u : 0x0102u)) >> 8) & 3u;
         }
-        if (EDGE) {
+        if (CEDGE) {
             mb &= VMASK;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -154,7 +187,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
                     T val = e[0];
 #pragma unroll
                     for (int j = 1; j < N; ++j) if ((pact % N) == j) val = e[j];
-                    cur[v] = val;
+                    F[IN][v] = val;
                     const int pacol = SGN > 0 ? x0 + pl * V : (int)a.pitch - (x0 + pl * V) - V;
                     const int pcol = SGN > 0 ? x0 + pos : (int)a.pitch - 1 - (x0 + pos);
                     const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
@@ -167,59 +200,64 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
         rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
         issue();
 
-        const T cl = shfl_up1(cur[V - 1]), cr = shfl_down1(cur[0]);
+        HL[IN] = shfl_up1(F[IN][V - 1]);
+        HR[IN] = shfl_down1(F[IN][0]);
 
-        // ---- intermediates of row y-1 (centre fC, row below = cur)
-        T P1[V], Q1[V];
+        // ---- intermediates of row y-1 (centre F[IC], row below = F[IN]) -> P[IC], Q[IC]
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const T right = (v < V - 1) ? fC[v + 1] : R1;
-            const T dx = right - fC[v];                // f[i, j+1] - f[i, j]
-            const T dy = cur[v] - fC[v];               // f[i+1, j] - f[i, j]
+            const T right = (v < V - 1) ? F[IC][v + 1] : HR[IC];
+            const T dx = right - F[IC][v];             // f[i, j+1] - f[i, j]
+            const T dy = F[IN][v] - F[IC][v];          // f[i+1, j] - f[i, j]
             if (TV) {
-                const T inv = rsqrt_t(dx * dx + dy * dy + a.eps2);
-                P1[v] = dx * inv;                      // n_x
-                Q1[v] = dy * inv;                      // n_y
+                const T inv = rsqrt_t(fma(dx, dx, fma(dy, dy, a.eps2)));
+                P[IC][v] = dx * inv;                   // n_x
+                Q[IC][v] = dy * inv;                   // n_y
             } else {
-                P1[v] = dy;                            // ux (reference's "x" is the row direction)
-                Q1[v] = dx;                            // uy
+                P[IC][v] = dy;                         // ux (reference's "x" is the row direction)
+                Q[IC][v] = dx;                         // uy
             }
         }
 
-        // ---- emit row r = y-2 (centre fB)
+        // ---- emit row r = y-2 (centre F[IU]); its intermediates are P[IU], Q[IU], the row above
+        // them (y-3) sits in slot IN
         const int r = y - LAG;
-        const bool top = (r == rtop);
-        T Pl = shfl_up1(P2[V - 1]);
-        T Ql = TV ? T(0) : shfl_up1(Q2[V - 1]);
+        if (REDGE) {
+            if (r == rtop) {                           // reflect-101 of the intermediate: [-1] := [1]
+#pragma unroll
+                for (int v = 0; v < V; ++v) { P[IN][v] = P[IC][v]; Q[IN][v] = Q[IC][v]; }
+            }
+        }
+        const T Pl = shfl_up1(P[IU][V - 1]);
+        const T Ql = TV ? T(0) : shfl_up1(Q[IU][V - 1]);
         T Pr = T(0), Qr = T(0);
-        if (EDGE) { Pr = shfl_down1(P2[0]); if (!TV) Qr = shfl_down1(Q2[0]); }
+        if (CEDGE) { Pr = shfl_down1(P[IU][0]); if (!TV) Qr = shfl_down1(Q[IU][0]); }
         const unsigned kb = (mhist >> (LAG * V)) & VMASK;
         T res[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            T pl = (v > 0) ? P2[v - 1] : Pl;
-            T ql = (v > 0) ? Q2[v - 1] : Ql;
-            if (EDGE && col0 + v == a.clo) {           // reflect-101 of the intermediate: [-1] := [1]
-                pl = (v < V - 1) ? P2[v + 1] : Pr;
-                ql = (v < V - 1) ? Q2[v + 1] : Qr;
+            T pl = (v > 0) ? P[IU][v - 1] : Pl;
+            T ql = (v > 0) ? Q[IU][v - 1] : Ql;
+            if (CEDGE && col0 + v == a.clo) {          // reflect-101 of the intermediate: [-1] := [1]
+                pl = (v < V - 1) ? P[IU][v + 1] : Pr;
+                ql = (v < V - 1) ? Q[IU][v + 1] : Qr;
             }
-            const T pu = top ? P1[v] : P3[v];
-            const T qu = top ? Q1[v] : Q3[v];
-            T step;
+            T stp;
             if (TV) {
-                step = (P2[v] - pl) + (Q2[v] - qu);
+                stp = (P[IU][v] - pl) + (Q[IU][v] - Q[IN][v]);
             } else {
-                const T uxx = P2[v] - pu, uxy = P2[v] - pl, uyx = Q2[v] - qu, uyy = Q2[v] - ql;
-                T v0 = fC[v] - fA[v];
-                const T fl = (v > 0) ? fB[v - 1] : L2, fr = (v < V - 1) ? fB[v + 1] : R2;
-                T v1 = fr - fl;
-                const T inv = rsqrt_t(v0 * v0 + v1 * v1 + T(1e-15));
-                v0 *= inv;
-                v1 *= inv;
-                step = (uxx * v0) * v0 + (uyy * v1) * v1 + ((uxy + uyx) * v0) * v1;
+                const T uxx = P[IU][v] - P[IN][v], uxy = P[IU][v] - pl;
+                const T uyx = Q[IU][v] - Q[IN][v], uyy = Q[IU][v] - ql;
+                const T fl = (v > 0) ? F[IU][v - 1] : HL[IU], fr = (v < V - 1) ? F[IU][v + 1] : HR[IU];
+                T w0 = v0[v];
+                T w1 = fr - fl;
+                const T inv = rsqrt_t(fma(w0, w0, fma(w1, w1, T(1e-15))));
+                w0 *= inv;
+                w1 *= inv;
+                stp = (uxx * w0) * w0 + (uyy * w1) * w1 + ((uxy + uyx) * w0) * w1;
             }
-            const T c = fB[v];
-            const T cand = c + dt * step;
+            const T c = F[IU][v];
+            const T cand = c + dt * stp;
             res[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
         }
         if (NORM) {
@@ -227,7 +265,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     if (col0 + v >= a.clo && col0 + v < a.chi) {
-                        const double dd = (double)(T)(res[v] - fB[v]);
+                        const double dd = (double)(T)(res[v] - F[IU][v]);
                         n_d2 += dd * dd;
                         n_f2 += (double)res[v] * (double)res[v];
                         const double ad = fabs(dd);
@@ -250,20 +288,23 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
             }
         }
         dptr += rstep;
+    };
 
-        // ---- rotate
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            fA[v] = fB[v]; fB[v] = fC[v]; fC[v] = cur[v];
-            P3[v] = P2[v]; Q3[v] = Q2[v]; P2[v] = P1[v]; Q2[v] = Q1[v];
-        }
-        L2 = L1; R2 = R1; L1 = cl; R1 = cr;
+    for (int y = ybeg; y < ystop; y += 3) {
+        step(Phase<0>(), y);
+        if (y + 1 < ystop) step(Phase<1>(), y + 1);
+        if (y + 2 < ystop) step(Phase<2>(), y + 2);
     }
     cp_async_wait<0>();
 }
 
+// Register budget: ptxas left to itself settles on 80 registers for TV and spills the loop bounds to
+// local memory (an LDL on the loop's critical path, profiles/r02_ncu_full_tv_f64_v2_summary.txt);
+// asking for MINB resident CTAs instead caps it at 65536 / (128 MINB) registers without spills.
+template <typename T, int METHOD> struct NLBudget { static constexpr int MINB = (METHOD == HMI_TV) ? 5 : 4; };
+
 template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM>
-__global__ void __launch_bounds__(WPB * 32) stream_nl_kernel(const StreamNLArgs<T> a)
+__global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD>::MINB) stream_nl_kernel(const StreamNLArgs<T> a)
 {
     typedef GeoNL<T, V> G;
     extern __shared__ __align__(16) unsigned char ring_all[];
@@ -272,21 +313,40 @@ __global__ void __launch_bounds__(WPB * 32) stream_nl_kernel(const StreamNLArgs<
     const int wib = threadIdx.x >> 5;
     const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * D * G::SLOT;
     const long long gw = (long long)blockIdx.x * WPB + wib;
-    const int win = (int)(gw % a.nwin);
-    const int chunk = (int)(gw / a.nwin);
     double n_d2 = 0.0, n_f2 = 0.0, n_mx = 0.0, n_nan = 0.0;
 
-    if (chunk < a.nchunks) {
+    // warp -> (strip, chunk): the n_edge column-edge strips (first, last) run the general path, so
+    // they are scheduled first and in shorter chunks (see stream_pick_chunks in hmi_stream.cu)
+    int win, chunk, ch_rows;
+    bool valid;
+    const long long n_e = (long long)a.n_edge * a.nchunks_e;
+    if (gw < n_e) {
+        win = (int)(gw % a.n_edge) == 0 ? 0 : a.nwin - 1;
+        chunk = (int)(gw / a.n_edge);
+        ch_rows = a.chunk_rows_e;
+        valid = true;
+    } else {
+        const long long g = gw - n_e;
+        const int ni = a.nwin - a.n_edge;
+        valid = ni > 0 && g < (long long)ni * a.nchunks;
+        win = ni > 0 ? (a.n_edge ? 1 : 0) + (int)(g % ni) : 0;
+        chunk = ni > 0 ? (int)(g / ni) : 0;
+        ch_rows = a.chunk_rows;
+    }
+
+    if (valid) {
         const int x0 = a.cbase + win * G::S - G::HV;
-        const int y0 = a.row_lo + chunk * a.chunk_rows;
-        const int y1 = min(a.row_hi, y0 + a.chunk_rows);
+        const int y0 = a.row_lo + chunk * ch_rows;
+        const int y1 = min(a.row_hi, y0 + ch_rows);
         const bool col_edge = (x0 < a.clo) || (x0 + 32 * V > a.chi);
         const bool row_edge = (y0 - 1 < 0 && a.top_border) || (y1 + 1 > a.rows && a.bottom_border) ||
                               (y0 - 1 < a.read_lo) || (y1 + 1 > a.read_hi) || (y0 <= 0 && a.top_border);
-        if (col_edge || row_edge)
-            stream_rows_nl<T, V, METHOD, SGN, D, true, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+        if (col_edge)
+            stream_rows_nl<T, V, METHOD, SGN, D, 2, NORM>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+        else if (row_edge)
+            stream_rows_nl<T, V, METHOD, SGN, D, 1, NORM>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows_nl<T, V, METHOD, SGN, D, false, NORM>(a, ring_s, lane, win, chunk, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 0, NORM>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -328,12 +388,26 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
         if (e != cudaSuccess) return e;
         cta_slots = stream_cta_slots((const void *)kern, WPB * 32, SMEM);
     }
-    (void)cta_slots;    // the wave-aware picker of hmi_stream.cu measured slower here (one sweep per launch is HBM bound)
-    a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
+    a.n_edge = 0;
+    a.nchunks_e = 0;
+    a.chunk_rows_e = 0;
+    if (l.chunk_rows == 0) {
+        a.n_edge = a.nwin >= 2 ? 2 : 1;
+        stream_pick_chunks(nrows, a.nwin, a.n_edge, 1, WPB, cta_slots, &a.chunk_rows, &a.chunk_rows_e);
+        a.nchunks_e = (nrows + a.chunk_rows_e - 1) / a.chunk_rows_e;
+    } else {
+        a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
+    }
     a.nchunks = (nrows + a.chunk_rows - 1) / a.chunk_rows;
-    const long long warps = (long long)a.nwin * a.nchunks;
+    const long long warps = (long long)a.n_edge * a.nchunks_e + (long long)(a.nwin - a.n_edge) * a.nchunks;
     const int blocks = (int)((warps + WPB - 1) / WPB);
     if (nblocks_out) *nblocks_out = blocks;
+    static int debug = -1;
+    if (debug < 0) debug = getenv("HMI_DEBUG") ? 1 : 0;
+    if (debug)
+        fprintf(stderr, "[hmi] stream_nl T=%d V=%d method=%d sgn=%d norm=%d: rows=%d nwin=%d chunk=%d x%d edge=%d x%d "
+                        "blocks=%d slots=%d (%.2f waves)\n", (int)sizeof(T), V, METHOD, SGN, (int)NORM, nrows, a.nwin,
+                a.chunk_rows, a.nchunks, a.chunk_rows_e, a.nchunks_e, blocks, cta_slots, (double)blocks / cta_slots);
     kern<<<blocks, WPB * 32, SMEM, st>>>(a);
     return cudaGetLastError();
 }

@@ -18,7 +18,7 @@ struct NLLaunch {
     int top_border, bottom_border;
     int method;                  // HMI_TV or HMI_AMLE
     int sgn;                     // +1 correlation ("opencv"), -1 convolution ("masked*")
-    int chunk_rows;              // <= 0 = auto
+    int chunk_rows;              // 0 = auto (wave-aware), < 0 = legacy auto rule
     int do_norm;
     T dt, eps2;
     double *partials;
@@ -37,6 +37,7 @@ struct StreamNLArgs {
     int clo, chi, cbase;         // canonical column range of the grid, first strip's origin
     int row_lo, row_hi, read_lo, read_hi, top_border, bottom_border;   // canonical
     int chunk_rows, nwin, nchunks;
+    int n_edge, nchunks_e, chunk_rows_e;   // column-edge strips: how many (listed first), their chunking
     T dt, eps2;
     double *partials;
     unsigned int *counter;

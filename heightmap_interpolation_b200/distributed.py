@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _capi as C
+from .inpainting.fd_pde_inpainter import _RangeView
 from .solver import Norm, Solver
 
 
@@ -261,19 +262,6 @@ def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=N
         return result, (r0, r1)
     finally:
         engine.close()
-
-
-class _RangeView:
-    """Stands in for the global grid in set_term_criteria(): only max() and min() are taken."""
-
-    def __init__(self, lo, hi):
-        self.lo, self.hi = lo, hi
-
-    def max(self, *a, **k):
-        return self.hi
-
-    def min(self, *a, **k):
-        return self.lo
 
 
 def _set_term_criteria_global(inpainter, interior, world, group, dev):

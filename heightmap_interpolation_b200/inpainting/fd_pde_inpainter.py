@@ -141,9 +141,57 @@ class FDPDEInpainter(ABC):
             from .multigrid import inpaint_multigrid
             return inpaint_multigrid(self, image, mask)
         self.print_msg("* Initializing the inpainting problem using the '{:s}' filler".format(self.init_with))
+        if self._can_fuse_init(image, mask):
+            return self._inpaint_fused_init(image, mask, out)
         image = self.initializer.initialize(image, mask)
         self.print_msg("* Optimization:")
         return self.inpaint_grid(image, mask, out)
+
+    # -- 'zeros' / 'mean' fused into the upload: the device fills its copy while a host thread
+    #    initialises the caller's array in place (what the reference does first, initializer.py:15-18)
+    def _can_fuse_init(self, image, mask):
+        return (self.init_with.lower() in ("zeros", "mean") and not self.print_progress
+                and isinstance(image, np.ndarray) and isinstance(mask, np.ndarray) and image.ndim == 2
+                and image.dtype in (np.float32, np.float64) and mask.dtype == np.bool_
+                and mask.shape == image.shape and image.flags.c_contiguous and image.flags.writeable
+                and mask.flags.c_contiguous and image.size >= (1 << 16) and self.term_check_iters > 0)
+
+    def _inpaint_fused_init(self, image, mask, out):
+        import ctypes
+        import threading
+        lib = C.lib()
+        code = C.HMI_F64 if image.dtype == np.float64 else C.HMI_F32
+        if self.init_with.lower() == "zeros":
+            value = 0.0
+        else:
+            m = ctypes.c_double()
+            C.check(lib.hmi_host_known_mean(image.ctypes.data, mask.ctypes.data, image.size, code, ctypes.byref(m)))
+            value = float(image.dtype.type(m.value))
+        if self.term_criteria == "absolute_percent":
+            # z-range of the *initialised* grid (fd_pde_inpainter.py:149-155) = known cells + fill value
+            lo, hi, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+            C.check(lib.hmi_host_known_minmax(image.ctypes.data, mask.ctypes.data, image.size, code,
+                                              ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(cnt)))
+            lo, hi = lo.value, hi.value
+            if cnt.value < image.size and not (lo != lo):
+                lo, hi = (min(lo, value), max(hi, value)) if cnt.value else (value, value)
+            self.set_term_criteria(_RangeView(image.dtype.type(lo), image.dtype.type(hi)))
+        else:
+            self.set_term_criteria(image)
+        self.print_msg("* Optimization:")
+        params = self._make_params(image.shape[0], image.shape[1], image.dtype)
+        filler = threading.Thread(target=lib.hmi_host_fill_unknown,
+                                  args=(image.ctypes.data, mask.ctypes.data, image.size, code, value))
+        filler.start()
+        try:
+            out, st = inpaint_host(params, image, mask, out, fill=value)
+        finally:
+            filler.join()
+        self._record(st.updates_done, st.last_diff, bool(st.converged), None, None)
+        self.history_.append((image.shape[0], image.shape[1], self.iterations_))
+        if not self.converged_:
+            print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
+        return out
 
     def _device(self):
         return 0 if self.device is None else int(self.device)
@@ -241,6 +289,19 @@ class FDPDEInpainter(ABC):
         if math.floor(number) == number:
             return 0
         return len("{:f}".format(number).split(".")[1])
+
+
+class _RangeView:
+    """Stands in for a grid in set_term_criteria(): only max() and min() are taken."""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = lo, hi
+
+    def max(self, *a, **k):
+        return self.hi
+
+    def min(self, *a, **k):
+        return self.lo
 
 
 def _check_inputs(image, mask):

@@ -160,9 +160,11 @@ class Solver:
         return self._lib.hmi_kernel_name(self._h).decode()
 
 
-def inpaint_host(params, image, mask, out=None):
+def inpaint_host(params, image, mask, out=None, fill=None):
     """hmi_inpaint_host: one call, host buffers in, host buffer out.  `out` (optional) is a
-    C-contiguous array of the grid's shape and dtype to receive the result, e.g. pinned memory."""
+    C-contiguous array of the grid's shape and dtype to receive the result, e.g. pinned memory.
+    `fill` (optional) = value the unknown cells take on the device after the upload
+    (hmi_inpaint_host_fill: the 'zeros' / 'mean' initialiser fused in)."""
     lib = C.lib()
     np_dtype = np.float64 if params.dtype == C.HMI_F64 else np.float32
     image = np.ascontiguousarray(image, dtype=np_dtype)
@@ -175,6 +177,10 @@ def inpaint_host(params, image, mask, out=None):
     elif out.shape != image.shape or out.dtype != image.dtype or not out.flags.c_contiguous:
         raise ValueError("out must be a C-contiguous array of the image's shape and dtype")
     st = C.HmiStatus()
-    C.check(lib.hmi_inpaint_host(ctypes.byref(params), image.ctypes.data, m8.ctypes.data,
-                                 out.ctypes.data, ctypes.byref(st)))
+    if fill is None:
+        C.check(lib.hmi_inpaint_host(ctypes.byref(params), image.ctypes.data, m8.ctypes.data,
+                                     out.ctypes.data, ctypes.byref(st)))
+    else:
+        C.check(lib.hmi_inpaint_host_fill(ctypes.byref(params), image.ctypes.data, m8.ctypes.data,
+                                          float(fill), out.ctypes.data, ctypes.byref(st)))
     return out, st

@@ -156,6 +156,13 @@ int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, 
 int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
                      hmi_status *status);
 
+/* hmi_inpaint_host with the 'zeros' / 'mean' initialiser fused in: after the upload the unknown cells
+ * (mask == 0) of the device copy are set to `fill_value`, so the caller can initialise its own host
+ * array (the reference does that in place, inpainting/initializer.py:15-18) concurrently with the
+ * upload instead of before it.  `image` itself is only read. */
+int hmi_inpaint_host_fill(const hmi_params *params, const void *image, const uint8_t *mask, double fill_value,
+                          void *out, hmi_status *status);
+
 /* Multi-GPU plumbing: device address and row pitch (bytes) of the current iterate and of the mask,
  * so the host layer can exchange ghost rows with NCCL (row 0 = first ghost row).  The addresses
  * change after every hmi_sweeps*() call (ping-pong). */
@@ -178,6 +185,13 @@ int hmi_host_known_mean(const void *image, const uint8_t *mask, int64_t n, int32
  * i.e. scipy.interpolate.griddata(method='nearest') over all known cells, inpainting/initializer.py:19-34. */
 int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *mask, size_t mask_pitch_bytes,
                           int32_t rows, int32_t cols, int32_t dtype, int32_t device);
+
+/* Minimum and maximum over the known cells (NaN-propagating like np.max / np.min) and their count,
+ * multi-threaded: with the fill value this gives the z-range of the initialised grid that
+ * set_term_criteria needs for 'absolute_percent' (inpainting/fd_pde_inpainter.py:149-155) without two
+ * more passes over the array. */
+int hmi_host_known_minmax(const void *image, const uint8_t *mask, int64_t n, int32_t dtype, double *min_out,
+                          double *max_out, int64_t *known_out);
 
 /* Pre-fault a freshly allocated host buffer with several threads (the result array of inpaint()). */
 int hmi_host_prefault(void *buf, size_t bytes);

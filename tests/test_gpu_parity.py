@@ -476,3 +476,35 @@ def test_inpaint_with_nearest_initialisation(golden_nearest):
     ref = g["nn00_solve"]
     assert np.array_equal(got[mask], ref[mask])
     assert range_err(got, ref) <= 1e-4
+
+
+# ------------------------------------------------------------------ fused 'zeros' / 'mean' initialiser
+@pytest.mark.parametrize("init,crit,dt", [("zeros", "relative", "f64"), ("mean", "absolute_percent", "f64"),
+                                          ("mean", "absolute_percent", "f32"), ("zeros", "absolute_percent", "f32")])
+def test_fused_initialiser_equals_host_initialiser(init, crit, dt):
+    """Large grids take hmi_inpaint_host_fill (device-side fill overlapped with the host's in-place
+    initialisation); it must be indistinguishable from initialising on the host first
+    (initializer.py:15-18 + set_term_criteria's z-range of the initialised grid, :149-155)."""
+    n = 320
+    img = synthetic.gaussian_hill(n, dtype=DTYPES[dt]) + DTYPES[dt](3.0)
+    mask = synthetic.mask_random(n, 0.35, seed=8)
+    img[~mask] = -7.5                                     # junk the initialiser must overwrite
+    opts = dict(update_step_size=0.2, term_criteria=crit, term_thres=1e-5, term_check_iters=10,
+                max_iters=500, init_with=init, convolver="opencv")
+    a = hmi.SobolevInpainter(**opts)
+    assert a._can_fuse_init(img, mask)
+    caller = img.copy()
+    got = a.inpaint(caller, mask)
+    ora = OracleInpainter("harmonic", **opts)
+    caller_ref = img.copy()
+    want = ora.inpaint(caller_ref, mask)
+    if init == "zeros":
+        assert np.array_equal(caller, caller_ref)         # caller's array initialised in place
+    else:   # the mean of a large grid is summed by threads in double, NumPy sums pairwise in the grid dtype
+        assert np.array_equal(caller[mask], caller_ref[mask])
+        assert np.allclose(caller, caller_ref, rtol=1e-13 if dt == "f64" else 1e-6, atol=0)
+        assert np.unique(caller[~mask]).size == 1
+    assert a.iterations_ == ora.updates_done and a.converged_ == ora.converged
+    assert float(a.term_thres) == pytest.approx(float(ora.term_thres), rel=1e-12 if dt == "f64" else 1e-6)
+    assert np.array_equal(got[mask], img[mask])
+    assert range_err(got, want) <= TOL[dt]

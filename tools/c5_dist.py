@@ -3,7 +3,7 @@ synthetic bathymetry grid with 40 % missing cells, row-slab sharded (strong scal
 fixed, each rank holds rows/world of it and never sees the rest).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        tools/c5_dist.py [--n 32768] [--dtypes f32,f64] [--methods harmonic,ccst] [--thres 1e-5]
+        tools/c5_dist.py [--size 32768] [--dtypes f32,f64] [--methods harmonic,ccst] [--thres 1e-5]
 
 Per (method, dtype) rank 0 prints one JSON line: stop iteration, wall time of the whole solve
 (upload + sweeps + checks + download, max over ranks), GLUPS, the per-GPU fraction of the HBM
@@ -35,7 +35,7 @@ CASES = {"harmonic": (hmi.SobolevInpainter, dict(update_step_size=0.2), 1, 16),
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--size", dest="n", type=int, default=32768)
     ap.add_argument("--dtypes", default="f32,f64")
     ap.add_argument("--methods", default="harmonic,ccst")
     ap.add_argument("--thres", type=float, default=1e-5)
