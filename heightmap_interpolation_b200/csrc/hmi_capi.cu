@@ -180,7 +180,7 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
     int nblocks = 0;
     cudaError_t e;
     if (s->use_nl) {
-        if (k != 1) return fail(HMI_ERR_STATE, "the TV/AMLE kernel runs one sweep per launch");
+        if (k < 1 || k > hmi::STREAM_NL_MAX_K) return fail(HMI_ERR_STATE, "the TV/AMLE kernel fuses at most two sweeps");
         hmi::NLLaunch<T> l;
         memset(&l, 0, sizeof(l));
         l.src = src; l.dst = dst; l.mask = mask;
@@ -191,6 +191,7 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
         l.top_border = p.ghost_top == 0; l.bottom_border = p.ghost_bottom == 0;
         l.method = p.method; l.sgn = p.orientation;
         l.chunk_rows = s->chunk_rows;
+        l.k = k;
         l.do_norm = do_norm ? 1 : 0;
         l.dt = (T)p.dt; l.eps2 = (T)(p.epsilon * p.epsilon);
         l.partials = s->d_partials; l.counter = s->d_counter; l.result = s->d_result;
@@ -268,7 +269,7 @@ int do_sweeps(hmi_solver *s, long long n, bool norm_on_last, cudaStream_t st)
         if (k > s->tb) k = s->tb;
         // the streaming kernel fuses the convergence sums into a single-sweep launch: keep the
         // last sweep of a check window on its own
-        if (norm_on_last && s->use_stream && done + k == n && k > 1) k -= 1;
+        if (norm_on_last && (s->use_stream || s->use_nl) && done + k == n && k > 1) k -= 1;
         const long long after = n - (done + k);  // sweeps still to run after this block
         const int lo = p.ghost_top > 0 ? (int)(-after * s->radius) : 0;
         const int hi = p.rows + (p.ghost_bottom > 0 ? (int)(after * s->radius) : 0);
@@ -418,6 +419,13 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
         return fail(HMI_ERR_UNSUPPORTED, "streaming TV/AMLE kernel needs reflect-101 borders, no over-relaxation and a grid of at least 8x8");
     }
     s->use_nl = nl_ok && p.kernel != HMI_KERNEL_GENERIC;
+    if (s->use_nl) {
+        // two fused sweeps by default (profiles/r02_tune_tv_amle_k2.log); one on grids too small for the halo
+        int k = p.temporal_block > 0 ? p.temporal_block : 2;
+        if (k > hmi::STREAM_NL_MAX_K) k = hmi::STREAM_NL_MAX_K;
+        if (p.rows < 16 || p.cols < 16) k = 1;
+        s->tb = k;
+    }
 
     const int mb_gen = hmi::generic_max_blocks(s->phys_rows, p.cols);
     const int mb_str = hmi::stream_max_blocks(p.method, s->phys_rows, p.cols);
@@ -478,6 +486,12 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
         return HMI_OK;
     }
     if (!strcmp(key, "temporal_block")) {
+        if (s->use_nl) {
+            if (value < 1 || value > hmi::STREAM_NL_MAX_K || (value > 1 && (s->p.rows < 16 || s->p.cols < 16)))
+                return fail(HMI_ERR_BAD_ARG, "temporal_block out of range");
+            s->tb = (int)value;
+            return HMI_OK;
+        }
         if (!s->use_stream) return fail(HMI_ERR_UNSUPPORTED, "temporal_block applies to the streaming kernel");
         const int maxk = hmi::stream_max_k(s->p.method, s->p.dtype);
         const int min_dim = s->p.cols < s->p.rows ? s->p.cols : s->p.rows;

@@ -123,7 +123,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     // CCST with folded coefficients: f' = f + c2*(sum of h's four neighbours) + c3*h,
     //   c2 = -dt(1-t), c3 = dt*t - 4*c2      (== f + dt*(t*h - (1-t)*L h))
     const T c2 = -(dt * a.one_minus_tension);
-    const T c3 = dt * a.tension - T(4) * c2;
+    const T c3 = fma(T(-4), c2, dt * a.tension);
 
     // Each lane copies the aligned 4-byte mask word that holds its V mask bytes (V = 2: two lanes
     // fetch the same word), so no lane ever reads ring bytes another lane wrote — except the edge
@@ -324,21 +324,23 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                 // centre row F[s][IC] (row y-s-1), above F[s][IU], below rin
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
+                    // explicit fma: every instantiation (any K, V, code path) rounds identically, so a
+                    // solve does not depend on how its sweeps were cut into launches or slabs
                     const T c = F[s][IC][v];
-                    const T cand = c + dt * (s4[v] - T(4) * c);
+                    const T cand = fma(dt, fma(T(-4), c, s4[v]), c);
                     o[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
                 }
             } else {
                 // rin is row yy = y-2s of sweep s; hN = L f (row yy-1); output = sweep s+1 of row yy-2
 #pragma unroll
-                for (int v = 0; v < V; ++v) Hh[s][IN][v] = s4[v] - T(4) * F[s][IC][v];
+                for (int v = 0; v < V; ++v) Hh[s][IN][v] = fma(T(-4), F[s][IC][v], s4[v]);
                 sum4_row<T, V>(Hh[s][IU], Hh[s][IC], Hh[s][IN], HL[s], HR[s], s4);
                 HL[s] = shfl_up1(Hh[s][IN][V - 1]);
                 HR[s] = shfl_down1(Hh[s][IN][0]);
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const T c = F[s][IU][v];
-                    const T cand = (c + c2 * s4[v]) + c3 * Hh[s][IC][v];
+                    const T cand = fma(c3, Hh[s][IC][v], fma(c2, s4[v], c));
                     o[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
                 }
             }

@@ -65,7 +65,11 @@ __device__ __forceinline__ double rsqrt_t(double x)
 // clamping to the slab's memory, the "upper neighbour of row 0" rule); 2: ghost columns as well.
 // The row loop is unrolled by three so that the windows of f rows, lane halos and intermediate rows
 // rotate by register renaming: slot(row) = row mod 3.
-template <typename T, int V, int METHOD, int SGN, int D, int MODE, bool NORM>
+// K sweeps are fused as K chained stages (temporal blocking): stage s takes the row stage s-1 has just
+// emitted as its newest input row, so step y emits sweep K of row y - 2K and only that is stored.
+// One sweep consumes one column and one row of validity per side; the strip already carries a whole
+// lane (V cells) of halo per side, so K <= V costs no extra column overlap.
+template <typename T, int V, int METHOD, int SGN, int D, int MODE, bool NORM, int K>
 __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const unsigned ring_s, const int lane,
                                                const int win, const int y0, const int y1, double &n_d2,
                                                double &n_f2, double &n_mx, double &n_nan)
@@ -76,16 +80,20 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
     constexpr bool TV = (METHOD == HMI_TV);
     constexpr bool REDGE = MODE >= 1, CEDGE = MODE == 2;
     constexpr unsigned VMASK = (1u << V) - 1u;
-    constexpr int LAG = 2;                             // step y emits row y-2
+    constexpr int LAG = 2 * K;                         // step y emits sweep K of row y - 2K
+    static_assert(K >= 1 && K <= 2 && K <= V, "temporal block deeper than the lane halo");
+    static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
+    static_assert((LAG + 1) * V <= 32, "mask history does not fit 32 bits");
 
     const int x0 = a.cbase + win * S - HV;             // canonical column of lane 0, cell 0
     const int col0 = x0 + lane * V;                    // canonical column of this lane's cell 0
     const int acol = SGN > 0 ? col0 : (int)a.pitch - col0 - V;   // actual column of the lane's chunk
-    const int ybeg = y0 - 1, yend = y1 + 1;            // canonical rows fetched: [ybeg, yend)
+    const int ybeg = y0 - K, yend = y1 + K;            // canonical rows fetched: [ybeg, yend)
     const int ystop = y1 + LAG;                        // steps: [ybeg, ystop)
     const bool out_lane = (lane >= 1) && (lane < 31) && (col0 < a.chi) && (col0 + V > a.clo);
     const T dt = a.dt;
     const int rtop = a.top_border ? 0 : -0x40000000;   // canonical row whose upper neighbour is row 1
+    const int rbot = a.bottom_border ? a.rows : 0x40000000;   // first ghost row below the grid
 
     const int mcol = acol & ~3;
     const unsigned msh = (unsigned)(acol & 3) * 8u;
@@ -132,148 +140,198 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 #pragma unroll
     for (int u = 0; u < D - 1; ++u) issue();
 
-    // slot(row) = row mod 3:  f rows y-2, y-1, y (and y-3 until row y lands in its slot), their lane
-    // halos, and the intermediate rows y-3, y-2, y-1 (n = g/|g| for TV, ux/uy for AMLE)
-    T F[3][V], P[3][V], Q[3][V], HL[3], HR[3];
+    // per stage, slot(row) = row mod 3:  its input rows ys-2, ys-1, ys (and ys-3 until row ys lands in
+    // its slot), their lane halos, and the intermediate rows ys-3, ys-2, ys-1 (n = g/|g| for TV,
+    // ux/uy for AMLE); ys = y - 2s is the newest input row of stage s at step y
+    T F[K][3][V], P[K][3][V], Q[K][3][V], HL[K][3], HR[K][3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        HL[q] = HR[q] = T(0);
+    for (int s = 0; s < K; ++s)
 #pragma unroll
-        for (int v = 0; v < V; ++v) F[q][v] = P[q][v] = Q[q][v] = T(0);
-    }
+        for (int q = 0; q < 3; ++q) {
+            HL[s][q] = HR[s][q] = T(0);
+#pragma unroll
+            for (int v = 0; v < V; ++v) F[s][q][v] = P[s][q][v] = Q[s][q][v] = T(0);
+        }
     unsigned mhist = 0u;
     unsigned rofs = 0;
     T *dptr = a.dst + (long long)arow(ybeg - LAG) * a.pitch + acol;
 
     auto step = [&](auto ph, const int y) {
         constexpr int PH = decltype(ph)::value;
-        constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;   // rows y-2, y-1, y (and y-3)
-        // AMLE: v0 = f[r+1] - f[r-1] of the row emitted below, r = y-2; row y-3 still sits in slot IN
-        T v0[V];
-        if (!TV) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) v0[v] = F[IC][v] - F[IN][v];
-        }
-        cp_async_wait<D - 2>();
-        if (CEDGE) __syncwarp();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            T e[N];
-            lds16(ring_f + rofs + c * 512, e);
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-                const int act = c * N + q;             // actual element -> canonical cell
-                F[IN][SGN > 0 ? act : V - 1 - act] = e[q];
-            }
-        }
-        unsigned mb;                                   // canonical cell v -> bit V-1-v
-        {
-            const unsigned w = lds32(ring_m + rofs);
-            if (V == 4) mb = (w * (SGN > 0 ? 0x08040201u : 0x01020408u)) >> 24;
-            else mb = ((((w >> msh) & 0xffffu) * (SGN > 0 ? 0x0201u : 0x0102u)) >> 8) & 3u;
-        }
-        if (CEDGE) {
-            mb &= VMASK;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int c = col0 + v;
-                if (c < a.clo || c >= a.chi) {         // ghost column: value and mask of the mirror cell
-                    const int cm = (c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c;
-                    const int pos = max(0, min(32 * V - 1, cm - x0));
-                    const int pl = pos / V, pv = pos % V;
-                    const int pact = SGN > 0 ? pv : V - 1 - pv;            // actual element in lane pl
-                    T e[N];
-                    lds16(ring_s + rofs + (pact / N) * 512 + pl * 16, e);
-                    T val = e[0];
-#pragma unroll
-                    for (int j = 1; j < N; ++j) if ((pact % N) == j) val = e[j];
-                    F[IN][v] = val;
-                    const int pacol = SGN > 0 ? x0 + pl * V : (int)a.pitch - (x0 + pl * V) - V;
-                    const int pcol = SGN > 0 ? x0 + pos : (int)a.pitch - 1 - (x0 + pos);
-                    const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
-                    const unsigned kb = (w >> (8 * (pcol - (pacol & ~3)))) & 1u;
-                    mb = (mb & ~(1u << (V - 1 - v))) | (kb << (V - 1 - v));
-                }
-            }
-        }
-        mhist = (mhist << V) | mb;
-        rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
-        issue();
-
-        HL[IN] = shfl_up1(F[IN][V - 1]);
-        HR[IN] = shfl_down1(F[IN][0]);
-
-        // ---- intermediates of row y-1 (centre F[IC], row below = F[IN]) -> P[IC], Q[IC]
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const T right = (v < V - 1) ? F[IC][v + 1] : HR[IC];
-            const T dx = right - F[IC][v];             // f[i, j+1] - f[i, j]
-            const T dy = F[IN][v] - F[IC][v];          // f[i+1, j] - f[i, j]
-            if (TV) {
-                const T inv = rsqrt_t(fma(dx, dx, fma(dy, dy, a.eps2)));
-                P[IC][v] = dx * inv;                   // n_x
-                Q[IC][v] = dy * inv;                   // n_y
-            } else {
-                P[IC][v] = dy;                         // ux (reference's "x" is the row direction)
-                Q[IC][v] = dx;                         // uy
-            }
-        }
-
-        // ---- emit row r = y-2 (centre F[IU]); its intermediates are P[IU], Q[IU], the row above
-        // them (y-3) sits in slot IN
-        const int r = y - LAG;
-        if (REDGE) {
-            if (r == rtop) {                           // reflect-101 of the intermediate: [-1] := [1]
-#pragma unroll
-                for (int v = 0; v < V; ++v) { P[IN][v] = P[IC][v]; Q[IN][v] = Q[IC][v]; }
-            }
-        }
-        const T Pl = shfl_up1(P[IU][V - 1]);
-        const T Ql = TV ? T(0) : shfl_up1(Q[IU][V - 1]);
-        T Pr = T(0), Qr = T(0);
-        if (CEDGE) { Pr = shfl_down1(P[IU][0]); if (!TV) Qr = shfl_down1(Q[IU][0]); }
-        const unsigned kb = (mhist >> (LAG * V)) & VMASK;
+        constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;   // rows ys-2, ys-1, ys (and ys-3)
         T res[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            T pl = (v > 0) ? P[IU][v - 1] : Pl;
-            T ql = (v > 0) ? Q[IU][v - 1] : Ql;
-            if (CEDGE && col0 + v == a.clo) {          // reflect-101 of the intermediate: [-1] := [1]
-                pl = (v < V - 1) ? P[IU][v + 1] : Pr;
-                ql = (v < V - 1) ? Q[IU][v + 1] : Qr;
-            }
-            T stp;
-            if (TV) {
-                stp = (P[IU][v] - pl) + (Q[IU][v] - Q[IN][v]);
-            } else {
-                const T uxx = P[IU][v] - P[IN][v], uxy = P[IU][v] - pl;
-                const T uyx = Q[IU][v] - Q[IN][v], uyy = Q[IU][v] - ql;
-                const T fl = (v > 0) ? F[IU][v - 1] : HL[IU], fr = (v < V - 1) ? F[IU][v + 1] : HR[IU];
-                T w0 = v0[v];
-                T w1 = fr - fl;
-                const T inv = rsqrt_t(fma(w0, w0, fma(w1, w1, T(1e-15))));
-                w0 *= inv;
-                w1 *= inv;
-                stp = (uxx * w0) * w0 + (uyy * w1) * w1 + ((uxy + uyx) * w0) * w1;
-            }
-            const T c = F[IU][v];
-            const T cand = c + dt * stp;
-            res[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
-        }
-        if (NORM) {
-            if (out_lane && r >= y0 && r < y1 && r >= 0 && r < a.rows) {
+        for (int s = 0; s < K; ++s) {
+            const int ys = y - 2 * s;
+            // AMLE: w0 = f[r+1] - f[r-1] of the row emitted below, r = ys-2; row ys-3 still sits in slot IN
+            T v0[V];
+            if (!TV) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    if (col0 + v >= a.clo && col0 + v < a.chi) {
-                        const double dd = (double)(T)(res[v] - F[IU][v]);
-                        n_d2 += dd * dd;
-                        n_f2 += (double)res[v] * (double)res[v];
-                        const double ad = fabs(dd);
-                        if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
+                for (int v = 0; v < V; ++v) v0[v] = F[s][IC][v] - F[s][IN][v];
+            }
+            if (s == 0) {
+                cp_async_wait<D - 2>();
+                if (CEDGE) __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    T e[N];
+                    lds16(ring_f + rofs + c * 512, e);
+#pragma unroll
+                    for (int q = 0; q < N; ++q) {
+                        const int act = c * N + q;     // actual element -> canonical cell
+                        F[0][IN][SGN > 0 ? act : V - 1 - act] = e[q];
+                    }
+                }
+                unsigned mb;                           // canonical cell v -> bit V-1-v
+                {
+                    const unsigned w = lds32(ring_m + rofs);
+                    if (V == 4) mb = (w * (SGN > 0 ? 0x08040201u : 0x01020408u)) >> 24;
+                    else mb = ((((w >> msh) & 0xffffu) * (SGN > 0 ? 0x0201u : 0x0102u)) >> 8) & 3u;
+                }
+                if (CEDGE) {
+                    mb &= VMASK;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const int c = col0 + v;
+                        if (c < a.clo || c >= a.chi) { // ghost column: value and mask of the mirror cell
+                            const int cm = (c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c;
+                            const int pos = max(0, min(32 * V - 1, cm - x0));
+                            const int pl = pos / V, pv = pos % V;
+                            const int pact = SGN > 0 ? pv : V - 1 - pv;    // actual element in lane pl
+                            T e[N];
+                            lds16(ring_s + rofs + (pact / N) * 512 + pl * 16, e);
+                            T val = e[0];
+#pragma unroll
+                            for (int j = 1; j < N; ++j) if ((pact % N) == j) val = e[j];
+                            F[0][IN][v] = val;
+                            const int pacol = SGN > 0 ? x0 + pl * V : (int)a.pitch - (x0 + pl * V) - V;
+                            const int pcol = SGN > 0 ? x0 + pos : (int)a.pitch - 1 - (x0 + pos);
+                            const unsigned w = lds32(ring_s + rofs + ROW_BYTES + pl * 4);
+                            const unsigned kb = (w >> (8 * (pcol - (pacol & ~3)))) & 1u;
+                            mb = (mb & ~(1u << (V - 1 - v))) | (kb << (V - 1 - v));
+                        }
+                    }
+                }
+                mhist = (mhist << V) | mb;
+                rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
+                issue();
+            } else {
+                // newest input row of this stage = the row the previous stage has just emitted.  The
+                // reference re-applies reflect-101 to every sweep's field, and for these one-sided
+                // schemes a ghost cell does not evolve like its mirror image, so ghosts are re-imposed:
+#pragma unroll
+                for (int v = 0; v < V; ++v) F[s][IN][v] = res[v];
+                if (REDGE) {
+                    if (ys == rbot) {                  // first row below the grid := row rows-2 (slot IU)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) F[s][IN][v] = F[s][IU][v];
+                    }
+                }
+                if (CEDGE) {                           // ghost columns := their mirror columns (other lanes)
+                    T fix[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const int c = col0 + v;
+                        const bool ghost = (c < a.clo || c >= a.chi);
+                        const int cm = (c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c;
+                        const int pos = max(0, min(32 * V - 1, cm - x0));
+                        const int pl = pos / V, pv = pos % V;
+                        T val = F[s][IN][v];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            const T cand = __shfl_sync(0xffffffffu, F[s][IN][j], pl);
+                            if (ghost && pv == j) val = cand;
+                        }
+                        fix[v] = val;
+                    }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) F[s][IN][v] = fix[v];
+                }
+            }
+
+            HL[s][IN] = shfl_up1(F[s][IN][V - 1]);
+            HR[s][IN] = shfl_down1(F[s][IN][0]);
+
+            // ---- intermediates of row ys-1 (centre F[IC], row below = F[IN]) -> P[IC], Q[IC]
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const T right = (v < V - 1) ? F[s][IC][v + 1] : HR[s][IC];
+                const T dx = right - F[s][IC][v];      // f[i, j+1] - f[i, j]
+                const T dy = F[s][IN][v] - F[s][IC][v];   // f[i+1, j] - f[i, j]
+                if (TV) {
+                    const T inv = rsqrt_t(fma(dx, dx, fma(dy, dy, a.eps2)));
+                    P[s][IC][v] = dx * inv;            // n_x
+                    Q[s][IC][v] = dy * inv;            // n_y
+                } else {
+                    P[s][IC][v] = dy;                  // ux (reference's "x" is the row direction)
+                    Q[s][IC][v] = dx;                  // uy
+                }
+            }
+
+            // ---- emit row r = ys-2 (centre F[IU]); its intermediates are P[IU], Q[IU], the row above
+            // them (ys-3) sits in slot IN
+            const int r = ys - 2;
+            if (REDGE) {
+                if (r == rtop) {                       // reflect-101 of the intermediate: [-1] := [1]
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { P[s][IN][v] = P[s][IC][v]; Q[s][IN][v] = Q[s][IC][v]; }
+                    if (!TV && s > 0) {                // ... and of the field itself: f[-1] := f[1], so w0 = 0
+#pragma unroll
+                        for (int v = 0; v < V; ++v) v0[v] = T(0);
                     }
                 }
             }
+            const T Pl = shfl_up1(P[s][IU][V - 1]);
+            const T Ql = TV ? T(0) : shfl_up1(Q[s][IU][V - 1]);
+            T Pr = T(0), Qr = T(0);
+            if (CEDGE) { Pr = shfl_down1(P[s][IU][0]); if (!TV) Qr = shfl_down1(Q[s][IU][0]); }
+            const unsigned kb = (mhist >> ((2 * s + 2) * V)) & VMASK;
+            T out[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                T pl = (v > 0) ? P[s][IU][v - 1] : Pl;
+                T ql = (v > 0) ? Q[s][IU][v - 1] : Ql;
+                if (CEDGE && col0 + v == a.clo) {      // reflect-101 of the intermediate: [-1] := [1]
+                    pl = (v < V - 1) ? P[s][IU][v + 1] : Pr;
+                    ql = (v < V - 1) ? Q[s][IU][v + 1] : Qr;
+                }
+                T stp;
+                if (TV) {
+                    stp = (P[s][IU][v] - pl) + (Q[s][IU][v] - Q[s][IN][v]);
+                } else {
+                    const T uxx = P[s][IU][v] - P[s][IN][v], uxy = P[s][IU][v] - pl;
+                    const T uyx = Q[s][IU][v] - Q[s][IN][v], uyy = Q[s][IU][v] - ql;
+                    const T fl = (v > 0) ? F[s][IU][v - 1] : HL[s][IU];
+                    const T fr = (v < V - 1) ? F[s][IU][v + 1] : HR[s][IU];
+                    T w0 = v0[v];
+                    T w1 = fr - fl;
+                    const T inv = rsqrt_t(fma(w0, w0, fma(w1, w1, T(1e-15))));
+                    w0 *= inv;
+                    w1 *= inv;
+                    stp = (uxx * w0) * w0 + (uyy * w1) * w1 + ((uxy + uyx) * w0) * w1;
+                }
+                const T c = F[s][IU][v];
+                const T cand = c + dt * stp;
+                out[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
+            }
+            if (NORM) {
+                if (out_lane && r >= y0 && r < y1 && r >= 0 && r < a.rows) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if (col0 + v >= a.clo && col0 + v < a.chi) {
+                            const double dd = (double)(T)(out[v] - F[s][IU][v]);
+                            n_d2 += dd * dd;
+                            n_f2 += (double)out[v] * (double)out[v];
+                            const double ad = fabs(dd);
+                            if (ad == ad) n_mx = fmax(n_mx, ad); else n_nan = 1.0;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) res[v] = out[v];
         }
+        const int r = y - LAG;                         // res is sweep K of row y - 2K
         if (out_lane && r >= y0 && r < y1) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -301,10 +359,12 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 // Register budget: ptxas left to itself settles on 80 registers for TV and spills the loop bounds to
 // local memory (an LDL on the loop's critical path, profiles/r02_ncu_full_tv_f64_v2_summary.txt);
 // asking for MINB resident CTAs instead caps it at 65536 / (128 MINB) registers without spills.
-template <typename T, int METHOD> struct NLBudget { static constexpr int MINB = (METHOD == HMI_TV) ? 5 : 4; };
+template <typename T, int METHOD, int K> struct NLBudget {
+    static constexpr int MINB = K > 1 ? 3 : ((METHOD == HMI_TV) ? 5 : 4);
+};
 
-template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM>
-__global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD>::MINB) stream_nl_kernel(const StreamNLArgs<T> a)
+template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM, int K>
+__global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD, K>::MINB) stream_nl_kernel(const StreamNLArgs<T> a)
 {
     typedef GeoNL<T, V> G;
     extern __shared__ __align__(16) unsigned char ring_all[];
@@ -339,14 +399,14 @@ __global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD>::MINB) stream_nl
         const int y0 = a.row_lo + chunk * ch_rows;
         const int y1 = min(a.row_hi, y0 + ch_rows);
         const bool col_edge = (x0 < a.clo) || (x0 + 32 * V > a.chi);
-        const bool row_edge = (y0 - 1 < 0 && a.top_border) || (y1 + 1 > a.rows && a.bottom_border) ||
-                              (y0 - 1 < a.read_lo) || (y1 + 1 > a.read_hi) || (y0 <= 0 && a.top_border);
+        const bool row_edge = (y0 - K < 0 && a.top_border) || (y1 + K > a.rows && a.bottom_border) ||
+                              (y0 - K < a.read_lo) || (y1 + K > a.read_hi) || (y0 <= 0 && a.top_border);
         if (col_edge)
-            stream_rows_nl<T, V, METHOD, SGN, D, 2, NORM>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 2, NORM, K>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else if (row_edge)
-            stream_rows_nl<T, V, METHOD, SGN, D, 1, NORM>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 1, NORM, K>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows_nl<T, V, METHOD, SGN, D, 0, NORM>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 0, NORM, K>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -354,7 +414,7 @@ __global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD>::MINB) stream_nl
 // ------------------------------------------------------------------------------------------------
 // host side
 
-template <typename T, int V, int METHOD, int SGN, bool NORM>
+template <typename T, int V, int METHOD, int SGN, bool NORM, int K>
 static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nblocks_out)
 {
     typedef GeoNL<T, V> G;
@@ -381,7 +441,7 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     a.cbase = a.clo - (a.clo % V);
     a.nwin = (a.chi - a.cbase + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
-    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM>;
+    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM, K>;
     static int cta_slots = 0;
     if (cta_slots == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -393,7 +453,7 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     a.chunk_rows_e = 0;
     if (l.chunk_rows == 0) {
         a.n_edge = a.nwin >= 2 ? 2 : 1;
-        stream_pick_chunks(nrows, a.nwin, a.n_edge, 1, WPB, cta_slots, &a.chunk_rows, &a.chunk_rows_e);
+        stream_pick_chunks(nrows, a.nwin, a.n_edge, K, WPB, cta_slots, &a.chunk_rows, &a.chunk_rows_e);
         a.nchunks_e = (nrows + a.chunk_rows_e - 1) / a.chunk_rows_e;
     } else {
         a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
@@ -405,8 +465,8 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     static int debug = -1;
     if (debug < 0) debug = getenv("HMI_DEBUG") ? 1 : 0;
     if (debug)
-        fprintf(stderr, "[hmi] stream_nl T=%d V=%d method=%d sgn=%d norm=%d: rows=%d nwin=%d chunk=%d x%d edge=%d x%d "
-                        "blocks=%d slots=%d (%.2f waves)\n", (int)sizeof(T), V, METHOD, SGN, (int)NORM, nrows, a.nwin,
+        fprintf(stderr, "[hmi] stream_nl T=%d V=%d K=%d method=%d sgn=%d norm=%d: rows=%d nwin=%d chunk=%d x%d edge=%d x%d "
+                        "blocks=%d slots=%d (%.2f waves)\n", (int)sizeof(T), V, K, METHOD, SGN, (int)NORM, nrows, a.nwin,
                 a.chunk_rows, a.nchunks, a.chunk_rows_e, a.nchunks_e, blocks, cta_slots, (double)blocks / cta_slots);
     kern<<<blocks, WPB * 32, SMEM, st>>>(a);
     return cudaGetLastError();
@@ -427,10 +487,14 @@ int stream_nl_auto_chunk_rows(int nrows, int nwin)
 template <typename T, int V>
 static cudaError_t launch_nl_v(const NLLaunch<T> &l, cudaStream_t st, int *nb)
 {
-#define HMI_NL(M, SG)                                                              \
-    if (l.method == M && l.sgn == SG)                                              \
-        return l.do_norm ? launch_nl_one<T, V, M, SG, true>(l, st, nb)             \
-                         : launch_nl_one<T, V, M, SG, false>(l, st, nb);
+    if (l.do_norm && l.k != 1) return cudaErrorInvalidValue;   // the norm is fused into single-sweep launches
+#define HMI_NL(M, SG)                                                                  \
+    if (l.method == M && l.sgn == SG) {                                                \
+        if (l.do_norm) return launch_nl_one<T, V, M, SG, true, 1>(l, st, nb);          \
+        if (l.k == 1) return launch_nl_one<T, V, M, SG, false, 1>(l, st, nb);          \
+        if (l.k == 2) return launch_nl_one<T, V, M, SG, false, 2>(l, st, nb);          \
+        return cudaErrorInvalidValue;                                                  \
+    }
     HMI_NL(HMI_TV, 1) HMI_NL(HMI_TV, -1) HMI_NL(HMI_AMLE, 1) HMI_NL(HMI_AMLE, -1)
 #undef HMI_NL
     return cudaErrorInvalidValue;

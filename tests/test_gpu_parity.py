@@ -197,13 +197,15 @@ def test_stream_kernel_matches_oracle(method, tb, dt, vec, tma):
 @pytest.mark.parametrize("conv", ["opencv", "masked"])
 @pytest.mark.parametrize("method", ["tv", "amle"])
 @pytest.mark.parametrize("shape", [(211, 333), (64, 61), (40, 1030), (515, 70)])
-def test_tv_amle_stream_kernel_matches_oracle(method, conv, dt, shape):
-    """Both orientations, ragged strips/chunks, unknown cells on every edge and corner."""
+@pytest.mark.parametrize("tb", [1, 2])
+def test_tv_amle_stream_kernel_matches_oracle(method, conv, dt, shape, tb):
+    """Both orientations, ragged strips/chunks, unknown cells on every edge and corner; one sweep per
+    launch and two fused sweeps (every sweep's field gets its own reflect-101 ghosts)."""
     img, mask = _problem(shape[0], shape[1], DTYPES[dt])
     K = 5
     for chunk in (0, 29):
-        got, info = gpu_sweeps(method, conv, img, mask, K, kernel="stream", chunk_rows=chunk)
-        assert info[0] == "stream_nl" and info[2] == K
+        got, info = gpu_sweeps(method, conv, img, mask, K, kernel="stream", chunk_rows=chunk, tb=tb)
+        assert info[0] == "stream_nl" and info[1] == tb and info[2] == (K + tb - 1) // tb
         ref = oracle_sweeps(method, conv, img, mask, K)
         assert np.array_equal(got[mask], img[mask])
         err = range_err(got, ref)
