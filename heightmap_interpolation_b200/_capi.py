@@ -39,6 +39,11 @@ class HmiStatus(ctypes.Structure):
                 ("converged", ctypes.c_int32), ("checks", ctypes.c_int32)]
 
 
+class HmiBlendInfo(ctypes.Structure):
+    _fields_ = [("min", ctypes.c_double), ("max", ctypes.c_double),
+                ("has_nan", ctypes.c_int32), ("image_had_nan", ctypes.c_int32)]
+
+
 class HmiNorm(ctypes.Structure):
     _fields_ = [("sum_d2", ctypes.c_double), ("sum_f2", ctypes.c_double),
                 ("max_abs", ctypes.c_double), ("has_nan", ctypes.c_double)]
@@ -64,6 +69,8 @@ SYMBOLS = {
                                         ctypes.POINTER(HmiStatus)]),
     "hmi_inpaint_host_fill": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _vp, ctypes.c_double, _vp,
                                              ctypes.POINTER(HmiStatus)]),
+    "hmi_set_problem_host_blend": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                  ctypes.c_int32, ctypes.POINTER(HmiBlendInfo)]),
     "hmi_current_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_mask_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_host_fill_unknown": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, ctypes.c_double]),
@@ -75,6 +82,7 @@ SYMBOLS = {
     "hmi_host_prefault": (ctypes.c_int, [_vp, _sz]),
     "hmi_release_cache": (ctypes.c_int, []),
     "hmi_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64]),
+    "hmi_set_term_thres": (ctypes.c_int, [_vp, ctypes.c_double]),
     "hmi_temporal_block": (ctypes.c_int, [_vp]),
     "hmi_launch_count": (_i64, [_vp]),
     "hmi_kernel_name": (ctypes.c_char_p, [_vp]),

@@ -2,6 +2,7 @@
 // reference code each entry point replaces).  Host-side orchestration only: buffer ownership,
 // kernel selection, the temporal-block schedule and the reference's check cadence
 // (heightmap_interpolation/inpainting/fd_pde_inpainter.py:311-351).
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -180,7 +181,8 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
     int nblocks = 0;
     cudaError_t e;
     if (s->use_nl) {
-        if (k < 1 || k > hmi::STREAM_NL_MAX_K) return fail(HMI_ERR_STATE, "the TV/AMLE kernel fuses at most two sweeps");
+        if (k < 1 || k > hmi::stream_nl_max_k(p.method, p.dtype))
+            return fail(HMI_ERR_STATE, "the TV/AMLE kernel fuses at most two (fp32: three) sweeps");
         hmi::NLLaunch<T> l;
         memset(&l, 0, sizeof(l));
         l.src = src; l.dst = dst; l.mask = mask;
@@ -421,8 +423,9 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     s->use_nl = nl_ok && p.kernel != HMI_KERNEL_GENERIC;
     if (s->use_nl) {
         // two fused sweeps by default (profiles/r02_tune_tv_amle_k2.log); one on grids too small for the halo
+        const int maxk = hmi::stream_nl_max_k(p.method, p.dtype);
         int k = p.temporal_block > 0 ? p.temporal_block : 2;
-        if (k > hmi::STREAM_NL_MAX_K) k = hmi::STREAM_NL_MAX_K;
+        if (k > maxk) k = maxk;
         if (p.rows < 16 || p.cols < 16) k = 1;
         s->tb = k;
     }
@@ -487,7 +490,8 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
     }
     if (!strcmp(key, "temporal_block")) {
         if (s->use_nl) {
-            if (value < 1 || value > hmi::STREAM_NL_MAX_K || (value > 1 && (s->p.rows < 16 || s->p.cols < 16)))
+            const int maxk = hmi::stream_nl_max_k(s->p.method, s->p.dtype);
+            if (value < 1 || value > maxk || (value > 1 && (s->p.rows < 16 || s->p.cols < 16)))
                 return fail(HMI_ERR_BAD_ARG, "temporal_block out of range");
             s->tb = (int)value;
             return HMI_OK;
@@ -776,6 +780,90 @@ int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *
     return rc;
 }
 
+int hmi_set_problem_host_blend(hmi_solver *fine, const void *image, size_t image_pitch_bytes, const uint8_t *mask,
+                               size_t mask_pitch_bytes, hmi_solver *coarse, const int32_t *sx, const int32_t *sx1,
+                               const void *ax0, const void *ax1, const int32_t *sy, const int32_t *sy1,
+                               const void *by0, const void *by1, int32_t scrub_nan, hmi_blend_info *info)
+{
+    if (!fine || !coarse || !sx || !sx1 || !ax0 || !ax1 || !sy || !sy1 || !by0 || !by1 || !info)
+        return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (fine == coarse) return fail(HMI_ERR_BAD_ARG, "fine and coarse solver must differ");
+    if (fine->p.dtype != coarse->p.dtype || fine->p.device != coarse->p.device)
+        return fail(HMI_ERR_BAD_ARG, "fine and coarse level must share dtype and device");
+    if (fine->p.ghost_top || fine->p.ghost_bottom || coarse->p.ghost_top || coarse->p.ghost_bottom)
+        return fail(HMI_ERR_STATE, "the multigrid blend works on whole grids, not slabs");
+    if (!coarse->has_problem) return fail(HMI_ERR_STATE, "the coarse level has no solution yet");
+    int rc = hmi_set_problem_host(fine, image, image_pitch_bytes, mask, mask_pitch_bytes);
+    if (rc != HMI_OK) return rc;
+    const int rows = fine->p.rows, cols = fine->p.cols;
+    const size_t elem = fine->elem;
+    // tables: [sx | sx1 | sy | sy1] ints, then [ax0 | ax1 | by0 | by1] values, then partials and the NaN flag
+    const size_t n_int = 2 * (size_t)cols + 2 * (size_t)rows;
+    const size_t off_val = (n_int * sizeof(int) + 15) / 16 * 16;
+    const size_t n_val = n_int;
+    const size_t off_part = (off_val + n_val * elem + 15) / 16 * 16;
+    const int max_blocks = hmi::upsample_max_blocks(cols);
+    const size_t off_flag = off_part + (size_t)max_blocks * 3 * sizeof(double);
+    const size_t total = off_flag + 16;
+    char *d = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, total));
+    std::vector<char> h(off_part);
+    int *hi_ = reinterpret_cast<int *>(h.data());
+    memcpy(hi_, sx, cols * sizeof(int));
+    memcpy(hi_ + cols, sx1, cols * sizeof(int));
+    memcpy(hi_ + 2 * cols, sy, rows * sizeof(int));
+    memcpy(hi_ + 2 * cols + rows, sy1, rows * sizeof(int));
+    char *hv = h.data() + off_val;
+    memcpy(hv, ax0, cols * elem);
+    memcpy(hv + cols * elem, ax1, cols * elem);
+    memcpy(hv + 2 * cols * elem, by0, rows * elem);
+    memcpy(hv + (2 * cols + rows) * elem, by1, rows * elem);
+    cudaError_t e = cudaMemcpy(d, h.data(), off_part, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d + off_flag, 0, 16);
+    int nblocks = 0;
+    if (e == cudaSuccess) {
+        const int *di = reinterpret_cast<const int *>(d);
+        const char *dv = d + off_val;
+        double *dpart = reinterpret_cast<double *>(d + off_part);
+        int *dflag = reinterpret_cast<int *>(d + off_flag);
+        if (fine->p.dtype == HMI_F64)
+            e = hmi::launch_upsample_blend<double>(
+                (double *)fine->buf[0], fine->pitch, fine->mask, fine->mpitch, rows, cols,
+                (const double *)coarse->buf[coarse->cur], coarse->pitch, di, di + cols, (const double *)dv,
+                (const double *)dv + cols, di + 2 * cols, di + 2 * cols + rows, (const double *)dv + 2 * cols,
+                (const double *)dv + 2 * cols + rows, scrub_nan, dpart, dflag, &nblocks, nullptr);
+        else
+            e = hmi::launch_upsample_blend<float>(
+                (float *)fine->buf[0], fine->pitch, fine->mask, fine->mpitch, rows, cols,
+                (const float *)coarse->buf[coarse->cur], coarse->pitch, di, di + cols, (const float *)dv,
+                (const float *)dv + cols, di + 2 * cols, di + 2 * cols + rows, (const float *)dv + 2 * cols,
+                (const float *)dv + 2 * cols + rows, scrub_nan, dpart, dflag, &nblocks, nullptr);
+    }
+    std::vector<double> part;
+    int flag = 0;
+    if (e == cudaSuccess) {
+        part.resize((size_t)nblocks * 3);
+        e = cudaMemcpy(part.data(), d + off_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, d + off_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HMI_ERR_CUDA, "multigrid blend failed: %s", cudaGetErrorString(e));
+    }
+    double lo = INFINITY, hi = -INFINITY, nanv = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        lo = part[3 * b] < lo ? part[3 * b] : lo;
+        hi = part[3 * b + 1] > hi ? part[3 * b + 1] : hi;
+        nanv = part[3 * b + 2] > nanv ? part[3 * b + 2] : nanv;
+    }
+    info->min = nanv != 0.0 ? nan("") : lo;      // np.min / np.max propagate NaN
+    info->max = nanv != 0.0 ? nan("") : hi;
+    info->has_nan = nanv != 0.0 ? 1 : 0;
+    info->image_had_nan = flag;
+    return HMI_OK;
+}
+
 int hmi_current_grid(hmi_solver *s, void **grid_dev, size_t *pitch_bytes)
 {
     if (!s || !grid_dev || !pitch_bytes) return fail(HMI_ERR_BAD_ARG, "null argument");
@@ -807,6 +895,15 @@ int hmi_release_cache(void)
         cudaFree(b.ptr);
     }
     cudaSetDevice(prev);
+    return HMI_OK;
+}
+
+int hmi_set_term_thres(hmi_solver *s, double term_thres)
+{
+    if (!s) return fail(HMI_ERR_BAD_ARG, "null solver");
+    if (!(term_thres > 0.0) && term_thres == term_thres)     // NaN is allowed: it never terminates, as in the reference
+        return fail(HMI_ERR_BAD_ARG, "term_thres must be larger than zero");
+    s->p.term_thres = term_thres;
     return HMI_OK;
 }
 

@@ -122,6 +122,93 @@ cudaError_t launch_init_nearest(const T *img, long long pitch, const uint8_t *ma
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multigrid: coarse solution -> next finer level (fd_pde_inpainter.py:255-263)
+//   upscaled = cv2.resize(coarse, (cols, rows))            default INTER_LINEAR, half-pixel centres
+//   image    = upscaled * (~mask) + image * mask
+// The interpolation taps and weights of both axes come from the host (they are 1-D tables, computed
+// exactly as the host restatement does); every product and sum here is a separate IEEE rounding in
+// the same order as that restatement, and the blend is the reference's arithmetic one, so a NaN left
+// in an unknown cell of a decimated image poisons the level exactly as it does in the reference.
+namespace {
+
+template <typename T>
+__global__ void upsample_blend_kernel(T *__restrict__ f, long long pitch, const uint8_t *__restrict__ mask,
+                                      long long mpitch, int rows, int cols, const T *__restrict__ coarse,
+                                      long long cpitch, const int *__restrict__ sx, const int *__restrict__ sx1,
+                                      const T *__restrict__ ax0, const T *__restrict__ ax1,
+                                      const int *__restrict__ sy, const int *__restrict__ sy1,
+                                      const T *__restrict__ by0, const T *__restrict__ by1, int scrub_nan,
+                                      double *__restrict__ partials, int *__restrict__ nan_flag)
+{
+    typedef Op<T> O;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double lo = INFINITY, hi = -INFINITY, nanv = 0.0;
+    if (j < cols) {
+        const int x0 = sx[j], x1 = sx1[j];
+        const T a0 = ax0[j], a1 = ax1[j];
+        for (int i = blockIdx.y; i < rows; i += gridDim.y) {
+            const T *c0 = coarse + (long long)sy[i] * cpitch, *c1 = coarse + (long long)sy1[i] * cpitch;
+            const T t0 = O::add(O::mul(c0[x0], a0), O::mul(c0[x1], a1));
+            const T t1 = O::add(O::mul(c1[x0], a0), O::mul(c1[x1], a1));
+            const T up = O::add(O::mul(t0, by0[i]), O::mul(t1, by1[i]));
+            T img = f[(long long)i * pitch + j];
+            if (scrub_nan && img != img) { img = T(0); *nan_flag = 1; }
+            const T m = mask[(long long)i * mpitch + j] ? T(1) : T(0);
+            const T v = O::add(O::mul(up, T(1) - m), O::mul(img, m));
+            f[(long long)i * pitch + j] = v;
+            const double d = (double)v;
+            if (d != d) nanv = 1.0;
+            lo = d < lo ? d : lo;
+            hi = d > hi ? d : hi;
+        }
+    }
+    // block min / max / NaN flag -> one partial per block (folded on the host)
+    __shared__ double sh[3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nanv = fmax(nanv, __shfl_xor_sync(0xffffffffu, nanv, o));
+    }
+    if (lane == 0) { sh[0][warp] = lo; sh[1][warp] = hi; sh[2][warp] = nanv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 1; w < nw; ++w) {
+            lo = fmin(lo, sh[0][w]); hi = fmax(hi, sh[1][w]); nanv = fmax(nanv, sh[2][w]);
+        }
+        const long long b = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        partials[3 * b + 0] = lo; partials[3 * b + 1] = hi; partials[3 * b + 2] = nanv;
+    }
+}
+
+}  // namespace
+
+template <typename T>
+cudaError_t launch_upsample_blend(T *f, long long pitch, const uint8_t *mask, long long mpitch, int rows, int cols,
+                                  const T *coarse, long long cpitch, const int *sx, const int *sx1, const T *ax0,
+                                  const T *ax1, const int *sy, const int *sy1, const T *by0, const T *by1,
+                                  int scrub_nan, double *partials, int *nan_flag, int *nblocks, cudaStream_t st)
+{
+    const dim3 grid((cols + 127) / 128, rows < UPSAMPLE_MAX_GRID_Y ? rows : UPSAMPLE_MAX_GRID_Y);
+    *nblocks = (int)(grid.x * grid.y);
+    upsample_blend_kernel<T><<<grid, 128, 0, st>>>(f, pitch, mask, mpitch, rows, cols, coarse, cpitch, sx, sx1, ax0,
+                                                   ax1, sy, sy1, by0, by1, scrub_nan, partials, nan_flag);
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_upsample_blend<float>(float *, long long, const uint8_t *, long long, int, int,
+                                                  const float *, long long, const int *, const int *, const float *,
+                                                  const float *, const int *, const int *, const float *,
+                                                  const float *, int, double *, int *, int *, cudaStream_t);
+template cudaError_t launch_upsample_blend<double>(double *, long long, const uint8_t *, long long, int, int,
+                                                   const double *, long long, const int *, const int *,
+                                                   const double *, const double *, const int *, const int *,
+                                                   const double *, const double *, int, double *, int *, int *,
+                                                   cudaStream_t);
+
 template cudaError_t launch_init_nearest<float>(const float *, long long, const uint8_t *, long long, int, int, int *,
                                                 long long, float *, long long, int *, cudaStream_t);
 template cudaError_t launch_init_nearest<double>(const double *, long long, const uint8_t *, long long, int, int,

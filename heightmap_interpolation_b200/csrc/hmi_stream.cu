@@ -465,7 +465,7 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
     a.chunk_rows_e = 0;
     if (a.chunk_rows == 0) {
         a.n_edge = a.nwin >= 2 ? 2 : 1;
-        stream_pick_chunks(nrows, a.nwin, a.n_edge, G::H + G::SK * (K - 1), WPB, cta_slots, &a.chunk_rows,
+        stream_pick_chunks(nrows, a.nwin, a.n_edge, G::H + G::SK * (K - 1), WPB, cta_slots, 1.7, &a.chunk_rows,
                            &a.chunk_rows_e);
         a.nchunks_e = (nrows + a.chunk_rows_e - 1) / a.chunk_rows_e;
     } else if (a.chunk_rows < 0) {
@@ -495,18 +495,19 @@ int stream_cta_slots(const void *kernel, int threads, size_t smem)
     return sms * occ;
 }
 
-void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, int *chunk_rows,
-                        int *chunk_rows_edge)
+void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, double edge_cost,
+                        int *chunk_rows, int *chunk_rows_edge)
 {
     // Wave-aware chunk heights.  Every warp streams (chunk + 2*halo) rows plus a pipeline fill and
     // the launch takes ceil(CTAs / resident CTAs) rounds of that; a fixed chunk height leaves the
     // last round partly empty (4096^2, fp64 CCST: SMs idle for 22 % of the kernel,
     // profiles/r01_ncu_full_ccst_f64_k3_summary.txt).  Pick the chunk count that minimises
-    // rounds * rows-per-warp.  The column-edge strips run the general code path (~1.7x the
-    // instructions per row), so they get chunks 1.7x shorter and are scheduled first; without that
-    // a single full wave is slower than three ragged ones (profiles/r02_tune_skew_ab.log).
+    // rounds * rows-per-warp.  The column-edge strips run the general code path (`edge_cost` times
+    // the instructions per row: 1.7 here, 2 - 2.8 in hmi_stream_nl.cu), so they get chunks that much
+    // shorter and are scheduled first; without that a single full wave is slower than three ragged
+    // ones, because the whole launch waits for the two edge strips (profiles/r02_tune_skew_ab.log,
+    // profiles/r02_tune_tv_chunks.log).
     const int fill = 8;
-    const double edge_cost = 1.7;
     int lo = 4 * halo;
     if (lo < 24) lo = 24;
     if (lo > nrows) lo = nrows;

@@ -60,6 +60,18 @@ __device__ __forceinline__ double rsqrt_t(double x)
     return fma(y * e, fma(e, 0.375, 0.5), y);
 }
 
+// known ? c : cand.  With three fused fp32 stages the 12 predicate-based selects of a row step exhaust
+// ptxas's 7 predicate registers ("register allocation failed"), so that variant blends by bit mask.
+template <int K>
+__device__ __forceinline__ float select_known(unsigned known, float c, float cand)
+{
+    if (K < 3) return known ? c : cand;
+    const unsigned m = 0u - known;
+    return __uint_as_float((__float_as_uint(c) & m) | (__float_as_uint(cand) & ~m));
+}
+template <int K>
+__device__ __forceinline__ double select_known(unsigned known, double c, double cand) { return known ? c : cand; }
+
 // One warp, one strip, rows [y0, y1) of it, in canonical coordinates (see header).
 // MODE 0: interior (lean loop); 1: only the rows need care (reflect-101 at the global top/bottom,
 // clamping to the slab's memory, the "upper neighbour of row 0" rule); 2: ghost columns as well.
@@ -81,7 +93,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
     constexpr bool REDGE = MODE >= 1, CEDGE = MODE == 2;
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int LAG = 2 * K;                         // step y emits sweep K of row y - 2K
-    static_assert(K >= 1 && K <= 2 && K <= V, "temporal block deeper than the lane halo");
+    static_assert(K >= 1 && K <= 3 && K <= V, "temporal block deeper than the lane halo");
     static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
     static_assert((LAG + 1) * V <= 32, "mask history does not fit 32 bits");
 
@@ -312,7 +324,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
                 }
                 const T c = F[s][IU][v];
                 const T cand = c + dt * stp;
-                out[v] = ((kb >> (V - 1 - v)) & 1u) ? c : cand;
+                out[v] = select_known<K>((kb >> (V - 1 - v)) & 1u, c, cand);
             }
             if (NORM) {
                 if (out_lane && r >= y0 && r < y1 && r >= 0 && r < a.rows) {
@@ -360,7 +372,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 // local memory (an LDL on the loop's critical path, profiles/r02_ncu_full_tv_f64_v2_summary.txt);
 // asking for MINB resident CTAs instead caps it at 65536 / (128 MINB) registers without spills.
 template <typename T, int METHOD, int K> struct NLBudget {
-    static constexpr int MINB = K > 1 ? 3 : ((METHOD == HMI_TV) ? 5 : 4);
+    static constexpr int MINB = K > 2 ? 2 : (K > 1 ? 3 : ((METHOD == HMI_TV) ? 5 : 4));
 };
 
 template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM, int K>
@@ -453,7 +465,10 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     a.chunk_rows_e = 0;
     if (l.chunk_rows == 0) {
         a.n_edge = a.nwin >= 2 ? 2 : 1;
-        stream_pick_chunks(nrows, a.nwin, a.n_edge, K, WPB, cta_slots, &a.chunk_rows, &a.chunk_rows_e);
+        // general path / lean path, instructions per row (SASS): fp32 2.8, fp64 2.0; be generous — the edge
+        // strips are 2 of ~70 and come first
+        stream_pick_chunks(nrows, a.nwin, a.n_edge, K, WPB, cta_slots, V == 4 ? 3.5 : 2.5, &a.chunk_rows,
+                           &a.chunk_rows_e);
         a.nchunks_e = (nrows + a.chunk_rows_e - 1) / a.chunk_rows_e;
     } else {
         a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
@@ -472,6 +487,11 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     return cudaGetLastError();
 }
 
+int stream_nl_max_k(int method, int dtype)
+{
+    return (method == HMI_TV && dtype == HMI_F32) ? 3 : 2;
+}
+
 int stream_nl_auto_chunk_rows(int nrows, int nwin)
 {
     // same rule as stream_auto_chunk_rows with a one-row halo: ~4 waves, within [32, 192] rows
@@ -484,6 +504,15 @@ int stream_nl_auto_chunk_rows(int nrows, int nwin)
     return (int)ch;
 }
 
+// three fused sweeps need three cells of lane halo: fp32 (V = 4) only; and TV only — ptxas cannot
+// allocate the predicates of the three-stage AMLE loop
+template <typename T, int V, int METHOD, int SGN>
+static cudaError_t launch_nl_k3(const NLLaunch<T> &l, cudaStream_t st, int *nb)
+{
+    if constexpr (V >= 3 && METHOD == HMI_TV) return launch_nl_one<T, V, METHOD, SGN, false, 3>(l, st, nb);
+    else return cudaErrorInvalidValue;
+}
+
 template <typename T, int V>
 static cudaError_t launch_nl_v(const NLLaunch<T> &l, cudaStream_t st, int *nb)
 {
@@ -493,6 +522,7 @@ static cudaError_t launch_nl_v(const NLLaunch<T> &l, cudaStream_t st, int *nb)
         if (l.do_norm) return launch_nl_one<T, V, M, SG, true, 1>(l, st, nb);          \
         if (l.k == 1) return launch_nl_one<T, V, M, SG, false, 1>(l, st, nb);          \
         if (l.k == 2) return launch_nl_one<T, V, M, SG, false, 2>(l, st, nb);          \
+        if (l.k == 3) return launch_nl_k3<T, V, M, SG>(l, st, nb);                     \
         return cudaErrorInvalidValue;                                                  \
     }
     HMI_NL(HMI_TV, 1) HMI_NL(HMI_TV, -1) HMI_NL(HMI_AMLE, 1) HMI_NL(HMI_AMLE, -1)

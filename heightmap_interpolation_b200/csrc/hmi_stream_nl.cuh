@@ -19,7 +19,7 @@ struct NLLaunch {
     int method;                  // HMI_TV or HMI_AMLE
     int sgn;                     // +1 correlation ("opencv"), -1 convolution ("masked*")
     int chunk_rows;              // 0 = auto (wave-aware), < 0 = legacy auto rule
-    int k;                       // sweeps fused per launch (1 or 2; the norm needs 1)
+    int k;                       // sweeps fused per launch (1..2, fp32 1..3; the norm needs 1)
     int do_norm;
     T dt, eps2;
     double *partials;
@@ -49,6 +49,6 @@ template <typename T>
 cudaError_t launch_stream_nl(const NLLaunch<T> &l, cudaStream_t st, int *nblocks_out);
 
 int stream_nl_auto_chunk_rows(int nrows, int nwin);
-constexpr int STREAM_NL_MAX_K = 2;
+int stream_nl_max_k(int method, int dtype);   // 2; TV fp32 (four cells of lane halo): 3
 
 }  // namespace hmi

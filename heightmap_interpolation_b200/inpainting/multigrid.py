@@ -6,8 +6,13 @@ initialiser applied to the coarsest level only (in place on a strided view, so i
 the caller's array exactly like the reference), the coarsest level solved with
 ``term_thres = orig * 2**num_levels``, then for each finer level L the coarser solution is
 up-sampled bilinearly (OpenCV ``cv2.resize`` default, half-pixel centres), blended into the unknown
-cells and relaxed with ``term_thres = orig * 2**L``.  Every level's relaxation runs on the B200
-through ``inpaint_grid``; the pyramid bookkeeping is O(cells) host work per level.
+cells and relaxed with ``term_thres = orig * 2**L``.
+
+Every level is relaxed on the B200 and the solution never leaves the device between levels: the
+bilinear up-sampling and the blend run in one kernel (``hmi_set_problem_host_blend``) from 1-D tap /
+weight tables built here exactly as OpenCV does, which also returns the z-range ``absolute_percent``
+needs.  What is left on the host per level is a contiguous copy of the decimated view and its upload.
+``resize_bilinear`` is the NumPy restatement of that kernel (tests pin both against cv2).
 """
 import math
 
@@ -89,22 +94,65 @@ def inpaint_multigrid(self, image, mask):
     self.print_start("[Pyramid Level {:d}] Inpainting...\\n".format(num_levels - 1))
     original_term_thres = self.term_thres
     self.term_thres = original_term_thres * 2 ** (num_levels)
-    inpainted_lower_scale = self.inpaint_grid(init_lower_scale, mask_pyramid[num_levels - 1] > 0)
-    self.print_end()
+    coarse_mask = mask_pyramid[num_levels - 1] > 0
     if num_levels == 1:
-        return inpainted_lower_scale
-    inpainted = inpainted_lower_scale
-    for level in range(num_levels - 2, -1, -1):
-        self.print_start("[Pyramid Level {:d}] Inpainting...\\n".format(level))
-        self.term_thres = original_term_thres * 2 ** level
-        image = image_pyramid[level]
-        mask = mask_pyramid[level]
-        upscaled = resize_bilinear(inpainted_lower_scale, image.shape[0], image.shape[1])
-        if level == 0 and np.any(np.isnan(image)):
-            image[np.isnan(image)] = 0
-        image = upscaled * (~mask) + image * mask
-        inpainted = self.inpaint_grid(image, mask)
+        inpainted = self.inpaint_grid(init_lower_scale, coarse_mask)
         self.print_end()
-        if level > 0:
-            inpainted_lower_scale = inpainted
-    return inpainted
+        return inpainted
+
+    from ..solver import Solver
+    from .fd_pde_inpainter import _RangeView, _check_inputs
+
+    def solve(solver, params, shape):
+        if self.print_progress:
+            done, diff, conv = self._loop(solver, params.criteria)
+        else:
+            st = solver.run()
+            done, diff, conv = st.updates_done, st.last_diff, bool(st.converged)
+        self._record(done, diff, conv, solver.kernel_name, solver.launch_count)
+        self.history_.append((shape[0], shape[1], self.iterations_))
+        if not self.converged_:
+            print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
+
+    coarse = None
+    try:
+        # coarsest level: plain inpaint_grid semantics, but the solution stays on the device
+        img_c, m_c = _check_inputs(init_lower_scale, coarse_mask)
+        self.set_term_criteria(img_c)
+        params = self._make_params(img_c.shape[0], img_c.shape[1], img_c.dtype)
+        coarse = Solver(params)
+        coarse.set_problem_host(img_c, m_c)
+        solve(coarse, params, img_c.shape)
+        self.print_end()
+        for level in range(num_levels - 2, -1, -1):
+            self.print_start("[Pyramid Level {:d}] Inpainting...\\n".format(level))
+            self.term_thres = original_term_thres * 2 ** level
+            image = image_pyramid[level]
+            mask = mask_pyramid[level]
+            img_c, m_c = _check_inputs(image, mask)
+            wt = np.float32 if img_c.dtype == np.float32 else np.float64
+            crows, ccols = coarse.params.rows, coarse.params.cols
+            xtab = _linear_coeffs(ccols, img_c.shape[1], wt)
+            ytab = _linear_coeffs(crows, img_c.shape[0], wt)
+            # provisional threshold; 'absolute_percent' rescales it once the blended grid's range is known
+            params = self._make_params(img_c.shape[0], img_c.shape[1], img_c.dtype,
+                                       term_thres=self.term_thres if self.term_thres > 0 else 1.0)
+            fine = Solver(params)
+            try:
+                info = fine.set_problem_host_blend(img_c, m_c, coarse, xtab, ytab, scrub_nan=(level == 0))
+            except Exception:
+                fine.close()
+                raise
+            if level == 0 and info.image_had_nan:      # the reference zeroes them in the caller's array (:259-260)
+                image[np.isnan(image)] = 0
+            self.set_term_criteria(_RangeView(img_c.dtype.type(info.min), img_c.dtype.type(info.max)))
+            fine.set_term_thres(self.term_thres)
+            params.term_thres = float(self.term_thres)
+            coarse.close()
+            coarse = fine
+            solve(coarse, params, img_c.shape)
+            self.print_end()
+        return coarse.get_result_host()
+    finally:
+        if coarse is not None:
+            coarse.close()

@@ -99,6 +99,32 @@ class Solver:
         C.check(self._lib.hmi_set_problem_host(self._h, image.ctypes.data, image.strides[0],
                                                m8.ctypes.data, m8.strides[0]))
 
+    def set_problem_host_blend(self, image, mask, coarse, xtab, ytab, scrub_nan=False):
+        """Multigrid: load this (finer) level and blend the up-sampled current iterate of `coarse`
+        into its unknown cells on the device (hmi_set_problem_host_blend).  xtab / ytab are the
+        (src0, src1, w0, w1) tables of cv2's INTER_LINEAR per axis.  Returns HmiBlendInfo."""
+        image = np.ascontiguousarray(image, dtype=self.np_dtype)
+        m8 = np.ascontiguousarray(mask).view(np.uint8) if mask.dtype == np.bool_ else \
+            np.ascontiguousarray(mask, dtype=np.uint8)
+        want = (self.params.rows, self.params.cols)
+        if image.shape != want or m8.shape != want:
+            raise ValueError("image/mask shape %s/%s, solver expects %s" % (image.shape, m8.shape, want))
+        tabs = []
+        for (s0, s1, w0, w1), n in ((xtab, want[1]), (ytab, want[0])):
+            tabs += [np.ascontiguousarray(s0, dtype=np.int32), np.ascontiguousarray(s1, dtype=np.int32),
+                     np.ascontiguousarray(w0, dtype=self.np_dtype), np.ascontiguousarray(w1, dtype=self.np_dtype)]
+            if any(t.shape != (n,) for t in tabs[-4:]):
+                raise ValueError("interpolation tables must have one entry per output column / row")
+        info = C.HmiBlendInfo()
+        C.check(self._lib.hmi_set_problem_host_blend(
+            self._h, image.ctypes.data, image.strides[0], m8.ctypes.data, m8.strides[0], coarse._h,
+            *[t.ctypes.data for t in tabs], 1 if scrub_nan else 0, ctypes.byref(info)))
+        return info
+
+    def set_term_thres(self, term_thres):
+        C.check(self._lib.hmi_set_term_thres(self._h, float(term_thres)))
+        self.params.term_thres = float(term_thres)
+
     def set_problem_device(self, image_ptr, image_pitch, mask_ptr, mask_pitch, stream=0):
         C.check(self._lib.hmi_set_problem_device(self._h, image_ptr, image_pitch, mask_ptr,
                                                  mask_pitch, stream))

@@ -163,6 +163,28 @@ int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t 
 int hmi_inpaint_host_fill(const hmi_params *params, const void *image, const uint8_t *mask, double fill_value,
                           void *out, hmi_status *status);
 
+/* Multigrid (FDPDEInpainter.inpaint_multigrid, inpainting/fd_pde_inpainter.py:255-264): load the next
+ * finer level into `fine` — upload its image and mask like hmi_set_problem_host, then replace the
+ * device copy by
+ *     image = cv2.resize(coarse solution, (cols, rows)) * (~mask) + image * mask
+ * where the coarse solution is the current iterate of `coarse` (it never leaves the device).  The
+ * bilinear taps (sx, sx1 / sy, sy1: source column / row pairs) and weights (ax0, ax1 / by0, by1, in
+ * the grid's dtype) are 1-D tables built by the host exactly as OpenCV's INTER_LINEAR does (half-pixel
+ * centres); products and sums are individually rounded in the order of the NumPy restatement.  With
+ * scrub_nan the NaNs of the uploaded image are zeroed first (level 0, :259-260) and
+ * info->image_had_nan reports whether there were any, so that the caller can do the same to its own
+ * array.  info->min/max are the extrema of the blended grid (NaN if it holds one): the z-range
+ * set_term_criteria needs for 'absolute_percent'. */
+typedef struct hmi_blend_info {
+    double min, max;
+    int32_t has_nan;          /* the blended grid contains a NaN */
+    int32_t image_had_nan;    /* the uploaded image contained a NaN (only checked with scrub_nan) */
+} hmi_blend_info;
+int hmi_set_problem_host_blend(hmi_solver *fine, const void *image, size_t image_pitch_bytes, const uint8_t *mask,
+                               size_t mask_pitch_bytes, hmi_solver *coarse, const int32_t *sx, const int32_t *sx1,
+                               const void *ax0, const void *ax1, const int32_t *sy, const int32_t *sy1,
+                               const void *by0, const void *by1, int32_t scrub_nan, hmi_blend_info *info);
+
 /* Multi-GPU plumbing: device address and row pitch (bytes) of the current iterate and of the mask,
  * so the host layer can exchange ghost rows with NCCL (row 0 = first ghost row).  The addresses
  * change after every hmi_sweeps*() call (ping-pong). */
@@ -203,6 +225,11 @@ int hmi_release_cache(void);
 /* Tuning knobs for tests and benchmarks: "chunk_rows" (rows per warp chunk of the streaming kernel,
  * 0 = wave-aware automatic choice, -1 = the older fixed rule) and "temporal_block" (sweeps fused per launch). */
 int hmi_set_option(hmi_solver *s, const char *key, int64_t value);
+
+/* Replace the stop threshold of hmi_run.  'absolute_percent' scales term_thres by the z-range of the
+ * initialised grid (set_term_criteria, inpainting/fd_pde_inpainter.py:149-155), which the multigrid
+ * driver only knows after the device-side blend (info->min/max of hmi_set_problem_host_blend). */
+int hmi_set_term_thres(hmi_solver *s, double term_thres);
 
 /* Introspection for tests and bench: sweeps fused per launch, kernels launched so far, and the
  * name of the kernel family the solver selected ("generic", "stream"). */

@@ -57,7 +57,7 @@ def main():
             for kernel in a.kernels.split(","):
                 tbs = [int(t) for t in a.tbs.split(",")] if kernel == "stream" else [1]
                 if method in ("tv", "amle"):
-                    tbs = [t for t in tbs if t <= 2] or [1]
+                    tbs = [t for t in tbs if t <= 3] or [1]
                 for tb in tbs:
                     if kernel == "stream" and method == "ccst" and tb > 4:
                         continue
