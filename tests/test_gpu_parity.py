@@ -512,3 +512,43 @@ def test_fused_initialiser_equals_host_initialiser(init, crit, dt):
     assert float(a.term_thres) == pytest.approx(float(ora.term_thres), rel=1e-12 if dt == "f64" else 1e-6)
     assert np.array_equal(got[mask], img[mask])
     assert range_err(got, want) <= TOL[dt]
+
+
+# ------------------------------------------------------------------ CLI glue
+def test_inpaint_work_areas_matches_reference_loop_body():
+    """apps/interpolate_netcdf4.py:176-212 with --backend b200: per work area crop to the bounding box,
+    NaN -> 0, fresh inpainter from the CLI namespace, paste back only the inpainted cells."""
+    import argparse
+    from heightmap_interpolation_b200.apps.interpolate import inpaint_work_areas
+    rows, cols = 150, 180
+    elev = synthetic.gaussian_hill((rows, cols)) + 5.0
+    mask_int = ~synthetic.mask_random((rows, cols), 0.3, seed=9)          # True == to interpolate
+    elev[mask_int] = np.nan                                               # what a NetCDF hole looks like
+    areas = np.zeros((rows, cols, 2), dtype=bool)
+    areas[10:70, 20:90, 0] = True
+    areas[80:140, 100:170, 1] = True
+    areas[100:120, 120:150, 1] = False                                    # a non-rectangular area
+    params = argparse.Namespace(subparser_name="ccst", update_step_size=0.01, tension=0.3, term_thres=1e-5,
+                                term_criteria="absolute_percent", term_check_iters=50, max_iters=5000,
+                                init_with="zeros", convolver="opencv", verbose=False)
+    got = inpaint_work_areas(elev, mask_int, areas, params)
+    # restatement with the CPU oracle in place of the inpainter
+    want = elev.copy()
+    for i in range(2):
+        a = areas[:, :, i]
+        r = np.where(a.any(axis=1))[0][[0, -1]]
+        c = np.where(a.any(axis=0))[0][[0, -1]]
+        sl = (slice(r[0], r[1] + 1), slice(c[0], c[1] + 1))
+        m = np.logical_or(~mask_int[sl], ~a[sl])
+        e = elev[sl].copy()
+        e[np.isnan(e)] = 0
+        o = OracleInpainter("ccst", update_step_size=0.01, tension=0.3, term_thres=1e-5,
+                            term_criteria="absolute_percent", term_check_iters=50, max_iters=5000,
+                            init_with="zeros", convolver="opencv")
+        res = o.inpaint(e, m)
+        want[sl][~m] = res[~m]
+    inside = mask_int & areas.any(axis=2)
+    assert np.array_equal(np.isnan(got), np.isnan(want))                   # holes outside the areas stay NaN
+    assert np.isnan(got[mask_int & ~areas.any(axis=2)]).all()
+    assert np.array_equal(got[~mask_int], elev[~mask_int])                 # reference cells untouched
+    assert range_err(got[inside], want[inside]) <= TOL["f64"]

@@ -259,3 +259,35 @@ def test_bilinear_resize_matches_opencv():
     a = np.arange(35.0).reshape(5, 7)
     h = halve_image(a)
     assert h.shape == (3, 4) and h.base is not None and h[1, 1] == a[2, 2]      # a view, like the reference
+
+
+def test_inpaint_work_areas_crop_and_paste():
+    """Loop body of the reference CLI (apps/interpolate_netcdf4.py:176-212) with a stand-in inpainter:
+    bounding-box crop, NaN -> 0 in the crop only, cells outside the area or not flagged stay untouched."""
+    from heightmap_interpolation_b200.apps.interpolate import inpaint_work_areas
+    elev = np.arange(30 * 40, dtype=np.float64).reshape(30, 40)
+    mask_int = np.zeros((30, 40), dtype=bool)
+    mask_int[5:25, 5:35] = True
+    elev[mask_int] = np.nan
+    area = np.zeros((30, 40, 1), dtype=bool)
+    area[8:20, 10:30, 0] = True
+    seen = {}
+
+    class Fake:
+        def inpaint(self, image, mask):
+            seen["shape"], seen["nan"] = image.shape, bool(np.isnan(image).any())
+            seen["known"] = int(mask.sum())
+            out = image.copy()
+            out[~mask] = 42.0
+            return out
+
+    got = inpaint_work_areas(elev, mask_int, area, inpainter_factory=Fake)
+    assert seen["shape"] == (12, 20) and not seen["nan"] and seen["known"] == 0
+    assert np.all(got[8:20, 10:30] == 42.0)
+    outside = mask_int.copy()
+    outside[8:20, 10:30] = False
+    assert np.isnan(got[outside]).all()                       # holes outside the work area stay holes
+    assert np.array_equal(got[~mask_int], elev[~mask_int])
+    assert np.isnan(elev[8:20, 10:30]).all()                  # the input is not modified
+    with pytest.raises(ValueError):
+        inpaint_work_areas(elev, mask_int[:10], area, inpainter_factory=Fake)
