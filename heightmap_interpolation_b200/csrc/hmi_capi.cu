@@ -175,6 +175,10 @@ template <typename T>
 int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip)
 {
     const hmi_params &p = s->p;
+    // Over-relaxation (fd_pde_inpainter.py:317-318): fnew = f(1-w) + (f + dt step)w = f + (w dt) step for
+    // every method, i.e. a larger step; the streaming kernels take it as such.  (The generic kernel
+    // keeps the reference's own expression.)
+    const double dt_eff = p.relaxation > 1.0 ? p.dt * p.relaxation : p.dt;
     const T *src = reinterpret_cast<const T *>(s->buf[s->cur]) + (long long)p.ghost_top * s->pitch;
     T *dst = reinterpret_cast<T *>(s->buf[s->cur ^ 1]) + (long long)p.ghost_top * s->pitch;
     const uint8_t *mask = s->mask + (long long)p.ghost_top * s->mpitch;
@@ -195,7 +199,7 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
         l.chunk_rows = s->chunk_rows;
         l.k = k;
         l.do_norm = do_norm ? 1 : 0;
-        l.dt = (T)p.dt; l.eps2 = (T)(p.epsilon * p.epsilon);
+        l.dt = (T)dt_eff; l.eps2 = (T)(p.epsilon * p.epsilon);
         l.partials = s->d_partials; l.counter = s->d_counter; l.result = s->d_result;
         e = hmi::launch_stream_nl<T>(l, st, &nblocks);
     } else if (s->use_stream) {
@@ -210,7 +214,7 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
         a.chunk_rows = s->chunk_rows;
         a.vec = s->vec;
         a.tma = s->tma;
-        a.dt = (T)p.dt; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
+        a.dt = (T)dt_eff; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
         a.do_norm = do_norm ? 1 : 0;
         a.partials = s->d_partials; a.counter = s->d_counter; a.result = s->d_result;
         e = hmi::launch_stream<T>(p.method, k, a, st, &nblocks);
@@ -388,12 +392,12 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
 
     // kernel selection
     const bool stream_ok = (p.method == HMI_HARMONIC || p.method == HMI_CCST) &&
-                           p.border == HMI_BORDER_REFLECT101 && !(p.relaxation > 1.0);
+                           p.border == HMI_BORDER_REFLECT101;
     int tb = 1;
     bool use_stream = false;
     if (p.kernel == HMI_KERNEL_STREAM && !stream_ok && (p.method == HMI_HARMONIC || p.method == HMI_CCST)) {
         delete s;
-        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel needs reflect-101 borders and no over-relaxation");
+        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel needs reflect-101 borders");
     }
     if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
         const int maxk = hmi::stream_max_k(p.method, p.dtype);
@@ -413,12 +417,12 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     }
     s->use_stream = use_stream;
     s->tb = tb;
-    // TV / AMLE: single-sweep streaming kernel (reflect-101, no over-relaxation, grid not tiny)
+    // TV / AMLE: streaming kernel (reflect-101, grid not tiny)
     const bool nl_ok = (p.method == HMI_TV || p.method == HMI_AMLE) && p.border == HMI_BORDER_REFLECT101 &&
-                       !(p.relaxation > 1.0) && p.rows >= 8 && p.cols >= 8;
+                       p.rows >= 8 && p.cols >= 8;
     if (p.kernel == HMI_KERNEL_STREAM && (p.method == HMI_TV || p.method == HMI_AMLE) && !nl_ok) {
         delete s;
-        return fail(HMI_ERR_UNSUPPORTED, "streaming TV/AMLE kernel needs reflect-101 borders, no over-relaxation and a grid of at least 8x8");
+        return fail(HMI_ERR_UNSUPPORTED, "streaming TV/AMLE kernel needs reflect-101 borders and a grid of at least 8x8");
     }
     s->use_nl = nl_ok && p.kernel != HMI_KERNEL_GENERIC;
     if (s->use_nl) {

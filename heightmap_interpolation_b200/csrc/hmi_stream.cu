@@ -78,7 +78,10 @@ struct Geo {
 template <bool SMALL> struct MaskHist { typedef unsigned long long type; };
 template <> struct MaskHist<true> { typedef unsigned type; };
 
-// Sum of the four neighbours of centre row b (rows above/below + lane halos)
+// Sum of the four neighbours of centre row b (rows above/below + lane halos).  The association
+// (up + dn) + (l + r) is invariant under mirroring either axis (IEEE addition commutes), so a ghost
+// cell loaded from its mirror cell evolves *bit for bit* like that cell through the fused sweeps and
+// the result does not depend on how the sweeps were cut into launches or slabs.
 template <typename T, int V>
 __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], const T (&dn)[V], T bl, T br,
                                          T (&out)[V])
@@ -87,7 +90,7 @@ __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], cons
     for (int v = 0; v < V; ++v) {
         const T l = (v > 0) ? b[v - 1] : bl;
         const T r = (v < V - 1) ? b[v + 1] : br;
-        out[v] = (up[v] + l) + (r + dn[v]);
+        out[v] = (up[v] + dn[v]) + (l + r);
     }
 }
 

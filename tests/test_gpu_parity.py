@@ -117,11 +117,19 @@ def test_ccst_tension_end_points_and_relaxation(golden_sweeps):
             got, _ = gpu_sweeps("ccst", "opencv", img, mask, 10, kernel=kernel,
                                 opts={"update_step_size": 0.01, "tension": float(t)})
             assert range_err(got, ref) <= TOL["f64"]
+    # over-relaxation: f + w (fnew - f) == a step of w dt; the generic kernel keeps the reference's
+    # expression, the streaming kernels take the larger step
     ref = golden_sweeps["sweeps__harmonic_relax15__opencv__f64__10"]
-    got, info = gpu_sweeps("harmonic", "opencv", img, mask, 10, relaxation=1.5)
-    assert info[0] == "generic"           # over-relaxation is served by the generic kernel
-    assert np.array_equal(got[mask], ref[mask])
-    assert range_err(got, ref) <= TOL["f64"]
+    for kernel, name in (("generic", "generic"), ("auto", "stream")):
+        got, info = gpu_sweeps("harmonic", "opencv", img, mask, 10, relaxation=1.5, kernel=kernel)
+        assert info[0] == name
+        assert np.array_equal(got[mask], ref[mask])
+        assert range_err(got, ref) <= TOL["f64"]
+    for method in ("ccst", "tv", "amle"):     # no reference fixture: streaming == generic (== oracle)
+        slow, _ = gpu_sweeps(method, "opencv", img, mask, 10, relaxation=1.3, kernel="generic")
+        fast, info = gpu_sweeps(method, "opencv", img, mask, 10, relaxation=1.3)
+        assert info[0].startswith("stream")
+        assert range_err(fast, slow) <= 1e-12, method
 
 
 def test_amle_convolve_in_1d_matches_reference(golden_sweeps):
@@ -324,6 +332,37 @@ def test_full_size_properties_4096():
     ref = oracle_sweeps("ccst", "opencv", img[-(c + 2 * K + 2):, -(c + 2 * K + 2):],
                         mask[-(c + 2 * K + 2):, -(c + 2 * K + 2):], K)
     assert range_err(fast[-c:, -c:], ref[-c:, -c:]) <= 1e-12
+
+
+def test_full_size_properties_16384_fp64_biharmonic():
+    """BASELINE config 4 size (biharmonic = CCST tension 0, and harmonic; 16384^2 fp64, 40 % random
+    mask, seed 2): known cells bit-exact, top-left and bottom-right corners equal the oracle, and a
+    row slab with ghost rows cut out of the middle (the multi-GPU data path) reproduces the whole-grid
+    rows bit for bit."""
+    n = 16384
+    mask = synthetic.mask_random(n, 0.40, seed=2)
+    img = synthetic.bathymetry(n, seed=7)
+    img[~mask] = 0
+    for method, extra, rad, K in (("ccst", dict(tension=0.0), 2, 6), ("harmonic", {}, 1, 12)):
+        opts = dict(METHOD_OPTS[method], **extra)
+        fast, info = gpu_sweeps(method, "opencv", img, mask, K, opts=opts)
+        assert info[0] == "stream"
+        assert np.array_equal(fast[mask], img[mask])
+        c, m = 64, rad * K + 2
+        ref = oracle_sweeps(method, "opencv", img[:c + m, :c + m], mask[:c + m, :c + m], K, **extra)
+        assert range_err(fast[:c, :c], ref[:c, :c]) <= 1e-12, method
+        ref = oracle_sweeps(method, "opencv", img[-(c + m):, -(c + m):], mask[-(c + m):, -(c + m):], K, **extra)
+        assert range_err(fast[-c:, -c:], ref[-c:, -c:]) <= 1e-12, method
+        # rows [r0, r1) as a slab with rad*K ghost rows on both sides: one block, no exchange needed
+        r0, r1, g = 6000, 6000 + 2048, rad * K
+        p = make_params(r1 - r0, n, np.float64, METHODS[method], orientation=1, dt=opts["update_step_size"],
+                        tension=opts.get("tension", 0.0), ghost_top=g, ghost_bottom=g)
+        with Solver(p) as s:
+            s.set_problem_host(img[r0 - g:r1 + g], mask[r0 - g:r1 + g])
+            s.sweeps(K)
+            slab = s.get_result_host()
+        assert np.array_equal(slab, fast[r0:r1]), method
+        del fast, slab
 
 
 def test_full_size_properties_8192_fp32_tv():

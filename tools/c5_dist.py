@@ -42,6 +42,9 @@ def main():
     ap.add_argument("--check-iters", type=int, default=50)
     ap.add_argument("--max-iters", type=int, default=3000)
     ap.add_argument("--crop", type=int, default=96)
+    ap.add_argument("--tension", type=float, default=0.3, help="CCST tension (0 = biharmonic, BASELINE config 4)")
+    ap.add_argument("--seed", type=int, default=3, help="mask seed (config 5: 3, config 4: 2)")
+    ap.add_argument("--exchange", default="", help="override exchange_every, e.g. harmonic=36,ccst=24")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -61,9 +64,14 @@ def main():
         dtype = np.float64 if dt == "f64" else np.float32
         for method in a.methods.split(","):
             cls, mopts, radius, E = CASES[method]
+            if method == "ccst":
+                mopts = dict(mopts, tension=a.tension)
+            for kv in filter(None, a.exchange.split(",")):
+                if kv.split("=")[0] == method:
+                    E = int(kv.split("=")[1])
             r_lo, r_hi, E = slab_rows_needed(n, world, rank, radius, E)
             t0 = time.perf_counter()
-            mask = synthetic.mask_random(n, 0.40, seed=3, row_range=(r_lo, r_hi))
+            mask = synthetic.mask_random(n, 0.40, seed=a.seed, row_range=(r_lo, r_hi))
             img = synthetic.bathymetry(n, seed=7, dtype=dtype, row_range=(r_lo, r_hi))
             img[~mask] = 0
             t_gen = time.perf_counter() - t0
@@ -129,7 +137,8 @@ def main():
                 glups = float(n) * n * its[0] / secs / 1e9
                 bpl = 17 if dt == "f64" else 9
                 print(json.dumps({
-                    "config": "C5 %s %dx%d 40%% missing %s" % (method, n, n, dt), "n_gpus": world,
+                    "config": "%s%s %dx%d 40%% missing (seed %d) %s" % (method, "" if method != "ccst" else " t=%g" % a.tension,
+                                                                       n, n, a.seed, dt), "n_gpus": world,
                     "iterations": its[0], "same_iterations_all_ranks": len(set(its)) == 1,
                     "converged": parts[0][5], "last_diff": parts[0][4], "solve_s": secs, "gen_s": t_gen,
                     "glups_e2e": glups, "hbm_roofline_frac_per_gpu_e2e": glups * bpl / peak / world,
