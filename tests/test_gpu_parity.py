@@ -310,6 +310,26 @@ def test_two_slabs_with_halo_exchange_equal_one_grid(method, kernel, block, over
     assert np.array_equal(got, whole), float(np.abs(got - whole).max())
 
 
+def test_baseline_config_1_stop_iterations():
+    """BASELINE config 1 (harmonic, 512^2 Gaussian hill, 30 % random mask seed 0, fp64, dt 0.2, relative):
+    with term_check_iters = 10 the unmodified reference stops after 31 updates at 1e-5 and 61 at 1e-8
+    (probe of the reference); so must the B200 path and the oracle, with filled cells
+    within 1e-10."""
+    n = 512
+    mask = synthetic.mask_random(n, 0.30, seed=0)
+    img = synthetic.zero_unknown(synthetic.gaussian_hill(n), mask)
+    for thres, want in ((1e-5, 31), (1e-8, 61)):
+        opts = dict(update_step_size=0.2, term_criteria="relative", term_thres=thres, term_check_iters=10,
+                    convolver="opencv")
+        inp = hmi.SobolevInpainter(**opts)
+        got = inp.inpaint(img.copy(), mask)
+        ora = OracleInpainter("harmonic", **opts)
+        ref = ora.inpaint(img.copy(), mask)
+        assert (inp.iterations_, ora.updates_done) == (want, want)
+        assert inp.converged_ and np.array_equal(got[mask], img[mask])
+        assert range_err(got, ref) <= TOL["f64"]
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_properties_4096():
     """BASELINE config 2 size (CCST, 4096^2 fp64, survey tracks): size-independent properties —
