@@ -14,6 +14,7 @@
 #include "hmi_stream.cuh"
 #include "hmi_stream_nl.cuh"
 #include "hmi_init.cuh"
+#include "hmi_xfer.cuh"
 
 namespace {
 
@@ -520,17 +521,12 @@ int hmi_set_problem_host(hmi_solver *s, const void *image, size_t image_pitch_by
         return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
     CUDA_TRY(cudaSetDevice(s->p.device));
     s->cur = 0;
-    // dense rows on both sides: one linear copy each (the 2-D path costs ~1 ms more on a 128 MiB grid)
-    if (image_pitch_bytes == wbytes && (size_t)s->pitch * s->elem == wbytes)
-        CUDA_TRY(cudaMemcpyAsync(s->buf[0], image, wbytes * s->phys_rows, cudaMemcpyHostToDevice, nullptr));
-    else
-        CUDA_TRY(cudaMemcpy2DAsync(s->buf[0], (size_t)s->pitch * s->elem, image, image_pitch_bytes, wbytes,
-                                   s->phys_rows, cudaMemcpyHostToDevice, nullptr));
-    if (mask_pitch_bytes == (size_t)s->p.cols && (size_t)s->mpitch == (size_t)s->p.cols)
-        CUDA_TRY(cudaMemcpyAsync(s->mask, mask, (size_t)s->p.cols * s->phys_rows, cudaMemcpyHostToDevice, nullptr));
-    else
-        CUDA_TRY(cudaMemcpy2DAsync(s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
-                                   s->phys_rows, cudaMemcpyHostToDevice, nullptr));
+    // pinned memory: straight DMA (one linear copy when dense); pageable memory (NumPy arrays): staged
+    // through pinned ring buffers by several host threads (hmi_xfer.cu)
+    CUDA_TRY(hmi::copy_h2d_2d(s->p.device, s->buf[0], (size_t)s->pitch * s->elem, image, image_pitch_bytes, wbytes,
+                              s->phys_rows));
+    CUDA_TRY(hmi::copy_h2d_2d(s->p.device, s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
+                              s->phys_rows));
     normalize_mask_kernel<<<592, 256>>>(s->mask, (size_t)s->phys_rows * s->mpitch);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(nullptr));    // the caller may reuse its host buffers on return
@@ -664,11 +660,7 @@ int hmi_get_result_host(hmi_solver *s, void *out, size_t out_pitch_bytes)
     CUDA_TRY(cudaSetDevice(s->p.device));
     CUDA_TRY(cudaDeviceSynchronize());
     const char *src = s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
-    if (out_pitch_bytes == wbytes && (size_t)s->pitch * s->elem == wbytes)
-        CUDA_TRY(cudaMemcpy(out, src, wbytes * s->p.rows, cudaMemcpyDeviceToHost));
-    else
-        CUDA_TRY(cudaMemcpy2D(out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows,
-                              cudaMemcpyDeviceToHost));
+    CUDA_TRY(hmi::copy_d2h_2d(s->p.device, out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows));
     return HMI_OK;
 }
 
@@ -754,10 +746,10 @@ int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *
         if ((e = cached_malloc(device, (void **)&d_mask, mbytes)) != cudaSuccess) break;
         if ((e = cached_malloc(device, (void **)&d_off, obytes)) != cudaSuccess) break;
         if ((e = cudaMalloc((void **)&d_status, sizeof(int))) != cudaSuccess) break;
-        if ((e = cudaMemcpy2D(d_img, (size_t)pitch * elem, image, image_pitch_bytes, wbytes, rows,
-                              cudaMemcpyHostToDevice)) != cudaSuccess) break;
-        if ((e = cudaMemcpy2D(d_mask, (size_t)mpitch, mask, mask_pitch_bytes, (size_t)cols, rows,
-                              cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = hmi::copy_h2d_2d(device, d_img, (size_t)pitch * elem, image, image_pitch_bytes, wbytes, rows)) !=
+            cudaSuccess) break;
+        if ((e = hmi::copy_h2d_2d(device, d_mask, (size_t)mpitch, mask, mask_pitch_bytes, (size_t)cols, rows)) !=
+            cudaSuccess) break;
         if (dtype == HMI_F64)
             e = hmi::launch_init_nearest<double>((const double *)d_img, pitch, d_mask, mpitch, rows, cols, d_off,
                                                  pitch, (double *)d_out, pitch, d_status, nullptr);
@@ -767,7 +759,7 @@ int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *
         if (e != cudaSuccess) break;
         if ((e = cudaMemcpy(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
         if (status != 0) break;
-        e = cudaMemcpy2D(image, image_pitch_bytes, d_out, (size_t)pitch * elem, wbytes, rows, cudaMemcpyDeviceToHost);
+        e = hmi::copy_d2h_2d(device, image, image_pitch_bytes, d_out, (size_t)pitch * elem, wbytes, rows);
     } while (0);
     if (e != cudaSuccess) {
         rc = fail(HMI_ERR_CUDA, "nearest initialiser failed: %s", cudaGetErrorString(e));
