@@ -291,3 +291,39 @@ def test_inpaint_work_areas_crop_and_paste():
     assert np.isnan(elev[8:20, 10:30]).all()                  # the input is not modified
     with pytest.raises(ValueError):
         inpaint_work_areas(elev, mask_int[:10], area, inpainter_factory=Fake)
+
+
+def test_host_known_minmax_matches_numpy():
+    """hmi_host_known_minmax (z-range of set_term_criteria, fd_pde_inpainter.py:149-155): min / max over
+    the known cells, NaN-propagating like np.max / np.min, threaded above 65536 cells."""
+    import ctypes
+    rng = np.random.default_rng(0)
+    for n, dt, code in ((1000, np.float64, C.HMI_F64), (300000, np.float32, C.HMI_F32)):
+        img = rng.standard_normal(n).astype(dt)
+        mask = rng.random(n) > 0.4
+        lo, hi, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        m8 = mask.view(np.uint8)
+        C.check(C.lib().hmi_host_known_minmax(img.ctypes.data, m8.ctypes.data, n, code, ctypes.byref(lo),
+                                              ctypes.byref(hi), ctypes.byref(cnt)))
+        assert (lo.value, hi.value, cnt.value) == (float(img[mask].min()), float(img[mask].max()), int(mask.sum()))
+        img[np.nonzero(mask)[0][n // 3]] = np.nan
+        C.check(C.lib().hmi_host_known_minmax(img.ctypes.data, m8.ctypes.data, n, code, ctypes.byref(lo),
+                                              ctypes.byref(hi), ctypes.byref(cnt)))
+        assert np.isnan(lo.value) and np.isnan(hi.value)
+        img[:] = np.nan
+        img[mask] = 1.0                                    # NaNs only in unknown cells do not count
+        C.check(C.lib().hmi_host_known_minmax(img.ctypes.data, m8.ctypes.data, n, code, ctypes.byref(lo),
+                                              ctypes.byref(hi), ctypes.byref(cnt)))
+        assert (lo.value, hi.value) == (1.0, 1.0)
+
+
+def test_slab_rows_needed_covers_ghosts():
+    from heightmap_interpolation_b200.distributed import slab_bounds, slab_rows_needed
+    rows, world = 1000, 4
+    for rank in range(world):
+        a, b, E = slab_rows_needed(rows, world, rank, radius=2, exchange_every=12)
+        r0, r1 = slab_bounds(rows, world)[rank]
+        assert E == 12
+        assert a == (r0 - 24 if rank > 0 else 0) and b == (r1 + 24 if rank < world - 1 else rows)
+    # the exchange depth is clamped so that the ghost rows fit inside the neighbouring slab
+    assert slab_rows_needed(40, 4, 1, radius=2, exchange_every=12)[2] == 4
