@@ -79,8 +79,8 @@ class CudaSlabEngine:
         edge rows are produced first on a side stream, `exchange()` is queued behind them on that
         stream, and the main stream only waits for it before the next block."""
         main = torch.cuda.current_stream(self.device)
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+        if self._side is None:     # high priority: the exchange should not queue behind the interior update
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
         self.solver.sweeps_overlap(n, main.cuda_stream, self._side.cuda_stream)
         with torch.cuda.stream(self._side):
             exchange()

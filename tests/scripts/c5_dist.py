@@ -3,7 +3,7 @@ synthetic bathymetry grid with 40 % missing cells, row-slab sharded (strong scal
 fixed, each rank holds rows/world of it and never sees the rest).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        tools/c5_dist.py [--size 32768] [--dtypes f32,f64] [--methods harmonic,ccst] [--thres 1e-5]
+        tests/scripts/c5_dist.py [--size 32768] [--dtypes f32,f64] [--methods harmonic,ccst] [--thres 1e-5]
 
 Per (method, dtype) rank 0 prints one JSON line: stop iteration, wall time of the whole solve
 (upload + sweeps + checks + download, max over ranks), GLUPS, the per-GPU fraction of the HBM
@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import heightmap_interpolation_b200 as hmi                                             # noqa: E402
 from heightmap_interpolation_b200 import synthetic                                     # noqa: E402

@@ -2,7 +2,7 @@
 Device-resident throughput + size-independent checks (known cells exact, corner crop vs oracle)."""
 import os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from heightmap_interpolation_b200 import _capi as C, synthetic
 from heightmap_interpolation_b200.solver import Solver, make_params
 from oracle.fdpde_oracle import OracleInpainter

@@ -1,6 +1,6 @@
 """BASELINE configs 2 and 3 solved to convergence on one GPU, end to end through the public API.
 
-    python tools/configs_run.py [--oracle]     # --oracle: also run the CPU oracle on config 2 (about 1-2 min)
+    python tests/scripts/configs_run.py [--oracle]     # --oracle: also run the CPU oracle on config 2 (about 1-2 min)
 
 Config 2: CCST (tension 0.3, dt 0.01), 4096^2 synthetic bathymetry with survey-track gaps, fp64,
           relative 1e-6 checked every 500 sweeps.  With --oracle the whole solve is repeated by the CPU
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import heightmap_interpolation_b200 as hmi                        # noqa: E402
 from heightmap_interpolation_b200 import synthetic                # noqa: E402
 

@@ -1,7 +1,7 @@
 """Compare stream kernel vs oracle and print the error pattern."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from heightmap_interpolation_b200 import _capi as C, synthetic
 from heightmap_interpolation_b200.solver import Solver, make_params
 from oracle.fdpde_oracle import OracleInpainter

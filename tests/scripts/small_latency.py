@@ -2,7 +2,7 @@
 BASELINE config 1 (harmonic, 512^2 Gaussian hill, 30 % random mask, fp64, relative 1e-5, check every 10)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import heightmap_interpolation_b200 as hmi
 from heightmap_interpolation_b200 import synthetic
 from oracle.fdpde_oracle import OracleInpainter

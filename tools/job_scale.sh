@@ -9,5 +9,5 @@ if [ "$N" != "1" ]; then
   timeout 600 $TR tools/dist_check.py > gpurun_out/dist_check$N.log 2>&1; echo "dist_check rc=$?"
   tail -2 gpurun_out/dist_check$N.log
 fi
-timeout 1200 $TR tools/c5_dist.py --size 32768 --dtypes f32,f64 > gpurun_out/c5_dist${N}_32768.log 2>&1; echo "c5 rc=$?"
+timeout 1200 $TR tests/scripts/c5_dist.py --size 32768 --dtypes f32,f64 > gpurun_out/c5_dist${N}_32768.log 2>&1; echo "c5 rc=$?"
 grep config gpurun_out/c5_dist${N}_32768.log | cut -c1-900
