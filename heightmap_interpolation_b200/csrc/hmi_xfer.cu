@@ -58,7 +58,6 @@ void worker(int t, int device, bool to_device, char *dev, size_t dev_pitch, char
     if ((*err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return;
     for (int b = 0; b < 2 && *err == cudaSuccess; ++b) *err = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
     const size_t nchunks = (rows + rpc - 1) / rpc;
-    const bool dense_host = host_pitch == width;
     auto stage_buf = [&](int b) { return stage + ((size_t)t * 2 + b) * kChunk; };
     auto host_copy = [&](char *dst, size_t dp, const char *src, size_t sp, size_t n) {
         if (dp == width && sp == width) { memcpy(dst, src, n * width); return; }
@@ -93,7 +92,6 @@ void worker(int t, int device, bool to_device, char *dev, size_t dev_pitch, char
             host_copy(host + r0 * host_pitch, host_pitch, stage_buf(b), width, n);
         }
     }
-    (void)dense_host;
     if (st) {
         const cudaError_t e = cudaStreamSynchronize(st);
         if (*err == cudaSuccess) *err = e;
