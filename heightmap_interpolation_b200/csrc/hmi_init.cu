@@ -3,7 +3,7 @@
 // Reference: Initializer.initialize with init_with='nearest'
 // (heightmap_interpolation/inpainting/initializer.py:19-34): scipy.interpolate.griddata(method=
 // 'nearest') over ALL known cells, i.e. every unknown cell takes the value of its Euclidean-nearest
-// known cell (a cKDTree query per cell; minutes of host time on a 4096^2 grid, and the CLI default,
+// known cell (a cKDTree query per cell; 3 s of host time on a 2048^2 grid, and the CLI default,
 // apps/apps_common.py:52).
 //
 // Here: an exact two-pass Euclidean nearest-known-cell search.

@@ -2,8 +2,8 @@
 
 `zeros` and `mean` run on the host in place, exactly as the reference does (the arrays are still on
 the host at this point).  `nearest` — the CLI default (apps/apps_common.py:52) — is a cKDTree query
-over *all* known cells in the reference (scipy.interpolate.griddata, :19-34), minutes of host time on
-a 4096^2 grid; here it is an exact Euclidean nearest-known-cell search on the B200
+over *all* known cells in the reference (scipy.interpolate.griddata, :19-34), 3 s of host time on a
+2048^2 grid; here it is an exact Euclidean nearest-known-cell search on the B200
 (csrc/hmi_init.cu, `hmi_init_nearest_host`), identical to SciPy wherever the nearest cell is unique
 and equidistant otherwise.  `linear`/`cubic` need a Delaunay triangulation of all known cells and
 stay SciPy calls, outside the accelerated path.  The `sobolev` initialiser is a
