@@ -12,9 +12,11 @@ namespace {
 
 int num_threads(int64_t n)
 {
-    if (n < (1 << 16)) return 1;
+    // one thread per million cells (starting a thread costs about as much as filling 200k cells)
     const unsigned hw = std::thread::hardware_concurrency();
-    return hw == 0 ? 4 : (hw > 16 ? 16 : (int)hw);
+    const int64_t cap = hw == 0 ? 4 : (hw > 16 ? 16 : (int64_t)hw);
+    const int64_t want = n >> 20;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
 template <typename T>

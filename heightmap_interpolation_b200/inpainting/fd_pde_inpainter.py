@@ -27,6 +27,8 @@ class FDPDEInpainter(ABC):
     """Abstract base of the explicit finite-difference PDE inpainters (reference class of the same name)."""
 
     METHOD = None  # hmi_method code, set by subclasses
+    # below this size the host fill (~0.14 ms per million cells) is cheaper than starting a thread for it
+    FUSE_INIT_MIN_CELLS = 1 << 21
 
     def __init__(self, **kwargs):
         super().__init__()
@@ -154,7 +156,7 @@ class FDPDEInpainter(ABC):
                 and isinstance(image, np.ndarray) and isinstance(mask, np.ndarray) and image.ndim == 2
                 and image.dtype in (np.float32, np.float64) and mask.dtype == np.bool_
                 and mask.shape == image.shape and image.flags.c_contiguous and image.flags.writeable
-                and mask.flags.c_contiguous and image.size >= (1 << 16) and self.term_check_iters > 0)
+                and mask.flags.c_contiguous and image.size >= self.FUSE_INIT_MIN_CELLS and self.term_check_iters > 0)
 
     def _inpaint_fused_init(self, image, mask, out):
         import ctypes

@@ -555,6 +555,7 @@ def test_fused_initialiser_equals_host_initialiser(init, crit, dt):
     opts = dict(update_step_size=0.2, term_criteria=crit, term_thres=1e-5, term_check_iters=10,
                 max_iters=500, init_with=init, convolver="opencv")
     a = hmi.SobolevInpainter(**opts)
+    a.FUSE_INIT_MIN_CELLS = 1 << 16                       # the fused path is normally taken above 2M cells
     assert a._can_fuse_init(img, mask)
     caller = img.copy()
     got = a.inpaint(caller, mask)
