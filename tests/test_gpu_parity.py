@@ -330,6 +330,30 @@ def test_baseline_config_1_stop_iterations():
         assert range_err(got, ref) <= TOL["f64"]
 
 
+@pytest.mark.parametrize("shape", [(2, 2), (3, 9), (7, 5), (9, 33), (16, 16), (17, 40)])
+@pytest.mark.parametrize("method", list(METHODS))
+def test_tiny_grids_through_the_public_api(method, shape):
+    """Grids smaller than the streaming kernels' halos fall back to the generic kernel inside the same
+    library (never to the CPU); every size must solve and match the oracle."""
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    mask = rng.random(shape) > 0.4
+    mask[0, 0] = True
+    img = (rng.standard_normal(shape) * 3 + 10)
+    img[~mask] = 0
+    opts = dict(METHOD_OPTS[method], convolver="opencv", term_criteria="relative", term_thres=1e-6,
+                term_check_iters=5, max_iters=60)
+    inp = CLASSES[method](**opts)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = inp.inpaint(img.copy(), mask)
+        ora = OracleInpainter(method, **opts)
+        ref = ora.inpaint(img.copy(), mask)
+    assert inp.iterations_ == ora.updates_done
+    assert np.array_equal(got[mask], img[mask])
+    assert range_err(got, ref) <= 1e-9
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_properties_4096():
     """BASELINE config 2 size (CCST, 4096^2 fp64, survey tracks): size-independent properties —
