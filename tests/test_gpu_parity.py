@@ -458,6 +458,29 @@ def test_multigrid_matches_reference(golden_multigrid):
         assert float(inp.term_thres) == pytest.approx(float(final_thres), rel=1e-6), key
 
 
+def test_multigrid_with_progress_output_equals_quiet_run(golden_multigrid):
+    """print_progress drives the levels through the Python loop (progress table, same semantics) instead
+    of hmi_run: same per-level iteration counts and bit-identical result."""
+    import contextlib
+    import io
+    g = golden_multigrid
+    mask, img = g["mask"], g["image__f64"]
+    opts = dict(METHOD_OPTS["harmonic"], convolver="opencv", term_criteria="relative", term_thres=1e-6,
+                term_check_iters=10, mgs_levels=3, mgs_min_res=20, init_with="zeros", max_iters=20000)
+    quiet = hmi.SobolevInpainter(**opts)
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = quiet.inpaint(img.copy(), mask)
+    loud = hmi.SobolevInpainter(print_progress=True, print_progress_iters=50, **opts)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        b = loud.inpaint(img.copy(), mask)
+    assert loud.history_ == quiet.history_ and len(quiet.history_) == 3
+    assert np.array_equal(a, b)
+    text = buf.getvalue()
+    assert "[Pyramid Level 2] Inpainting..." in text and "[Pyramid Level 0] Inpainting..." in text
+    assert text.count("| CONVERGED |") == 3
+
+
 def test_converged_ccst_tracks_512_matches_oracle():
     """A mid-size solve to convergence (BASELINE config 2 in small: CCST t=0.3, bathymetry, survey
     tracks): same stop iteration and last diff as the oracle, filled cells within 1e-10."""
