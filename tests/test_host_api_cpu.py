@@ -67,6 +67,28 @@ def test_no_cpu_fallback_without_a_device():
         inp.inpaint(np.zeros((8, 8)), np.ones((8, 8), dtype=bool))
 
 
+def test_nearest_and_multigrid_paths_fail_loudly_without_a_device():
+    """The new device-side paths (nearest initialiser, fused fill, multigrid chaining) have no CPU
+    fallback either; bad arguments are rejected before any CUDA call."""
+    import ctypes
+    import torch
+    lib = C.lib()
+    img, mask = np.zeros((8, 8)), np.ones((8, 8), dtype=np.uint8)
+    assert lib.hmi_init_nearest_host(None, 64, mask.ctypes.data, 8, 8, 8, C.HMI_F64, 0) == C.HMI_ERR_BAD_ARG
+    assert lib.hmi_init_nearest_host(img.ctypes.data, 8, mask.ctypes.data, 8, 8, 8, C.HMI_F64, 0) == C.HMI_ERR_BAD_ARG
+    assert b"pitch" in lib.hmi_last_error()
+    assert lib.hmi_set_term_thres(None, 1.0) == C.HMI_ERR_BAD_ARG
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hmi.SobolevInpainter(init_with="nearest").inpaint(np.zeros((8, 8)), np.eye(8, dtype=bool))
+    big = np.zeros((1500, 1500))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):       # fused zeros/mean path (>= 2M cells)
+        hmi.SobolevInpainter(init_with="mean").inpaint(big, np.ones(big.shape, dtype=bool))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hmi.SobolevInpainter(mgs_levels=2, mgs_min_res=20).inpaint(np.zeros((64, 64)), np.eye(64, dtype=bool))
+
+
 def test_constructor_defaults_and_get_config_match_reference():
     inp = hmi.SobolevInpainter()
     assert inp.get_config() == {
