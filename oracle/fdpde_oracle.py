@@ -112,6 +112,8 @@ class OracleInpainter:
         self.epsilon = kwargs.pop("epsilon", 1e-2)
         # amle_inpainter.py:26-37: scipy.ndimage.convolve1d (mode='reflect') on the whole grid
         self.convolve_in_1d = kwargs.pop("convolve_in_1d", False)
+        self.mgs_levels = kwargs.pop("mgs_levels", 1)
+        self.mgs_min_res = kwargs.pop("mgs_min_res", 100)
         if self.convolver_type.lower() not in CONVOLVERS:
             raise ValueError("Unknown convolver type '{:s}'".format(self.convolver_type))
         # results of the last solve (the reference only prints these)
@@ -181,8 +183,55 @@ class OracleInpainter:
         return out
 
     def inpaint(self, image, mask):
+        if getattr(self, "mgs_levels", 1) > 1:
+            return self.inpaint_multigrid(image, mask)
         image = self.initialize(image, mask)
         return self.inpaint_grid(image, mask)
+
+    def inpaint_multigrid(self, image, mask):
+        """fd_pde_inpainter.py:187-279 restated: stride-2 pyramid of views (misc/image_proc.py:4-12), the
+        initialiser on the coarsest level only (through the view, i.e. into the caller's array),
+        coarsest threshold orig * 2**num_levels, then per finer level cv2.resize (bilinear, restated in
+        `resize_bilinear` below), the arithmetic blend up*(~mask) + image*mask and orig * 2**level.
+        Records (rows, cols, updates) per level in self.history."""
+        import math
+        self.history = []
+        if image.shape[0] < self.mgs_min_res or image.shape[1] < self.mgs_min_res:
+            out = self.inpaint_grid(image, mask)            # :196-199: no initialiser on this path
+            self.history.append((image.shape[0], image.shape[1], self.updates_done))
+            return out
+        images, masks = [image], [mask]
+        num_levels = self.mgs_levels
+        for level in range(1, self.mgs_levels):
+            width = math.ceil(images[level - 1].shape[1] / 2)
+            height = math.ceil(images[level - 1].shape[0] / 2)
+            if width < self.mgs_min_res or height < self.mgs_min_res:
+                num_levels = level
+                break
+            img_rs = images[level - 1][0::2, 0::2]
+            images.append(img_rs)
+            m_rs = np.asarray(masks[level - 1], dtype="uint8")[0::2, 0::2]
+            masks.append(np.logical_and(m_rs, ~np.isnan(img_rs)))
+        init = self.initialize(images[num_levels - 1], masks[num_levels - 1])
+        original = self.term_thres
+        self.term_thres = original * 2 ** num_levels
+        coarse = self.inpaint_grid(init, masks[num_levels - 1] > 0)
+        self.history.append((init.shape[0], init.shape[1], self.updates_done))
+        if num_levels == 1:
+            return coarse
+        result = coarse
+        for level in range(num_levels - 2, -1, -1):
+            self.term_thres = original * 2 ** level
+            img, m = images[level], masks[level]
+            up = resize_bilinear(coarse, img.shape[0], img.shape[1])
+            if level == 0 and np.any(np.isnan(img)):
+                img[np.isnan(img)] = 0
+            blended = up * (~m) + img * m
+            result = self.inpaint_grid(blended, m)
+            self.history.append((img.shape[0], img.shape[1], self.updates_done))
+            if level > 0:
+                coarse = result
+        return result
 
 
 def nearest_init(image, mask, return_d2=False):
@@ -209,6 +258,37 @@ def nearest_init(image, mask, return_d2=False):
         image[i, j] = vals[key]
         d2[i, j] = dd[key]
     return (image, d2) if return_d2 else image
+
+
+def resize_bilinear(src, rows, cols):
+    """cv2.resize(src, (cols, rows)) with the default INTER_LINEAR (fd_pde_inpainter.py:255 passes no
+    interpolation argument): half-pixel centres, fx = (d + 0.5) * (ssize / dsize) - 0.5 clamped at both
+    ends, weights rounded to the image's own precision, columns first and then rows.  (OpenCV is a
+    third-party dependency absent from /root/reference; this is its published algorithm, and the
+    multigrid fixtures produced by the reference pin it.)"""
+    src = np.asarray(src)
+    wt = np.float32 if src.dtype == np.float32 else np.float64
+
+    def taps(ssize, dsize):
+        d = np.arange(dsize, dtype=np.float64)
+        f = (d + 0.5) * (float(ssize) / float(dsize)) - 0.5
+        i0 = np.floor(f).astype(np.int64)
+        f = f - i0
+        f[i0 < 0] = 0.0
+        i0[i0 < 0] = 0
+        hi = i0 >= ssize - 1
+        f[hi] = 0.0
+        i0[hi] = ssize - 1
+        i1 = np.minimum(i0 + 1, ssize - 1)
+        f = f.astype(wt)
+        return i0, i1, (wt(1.0) - f).astype(wt), f
+
+    x0, x1, a0, a1 = taps(src.shape[1], cols)
+    y0, y1, b0, b1 = taps(src.shape[0], rows)
+    s = src.astype(wt, copy=False)
+    tmp = s[:, x0] * a0[None, :] + s[:, x1] * a1[None, :]
+    out = tmp[y0, :] * b0[:, None] + tmp[y1, :] * b1[:, None]
+    return out.astype(src.dtype, copy=False)
 
 
 def dilate3x3(unknown):

@@ -133,3 +133,40 @@ def test_solve_from_reference_nearest_initialisation(golden_nearest):
     assert (o.updates_done, o.converged) == (int(upd), bool(int(term)))
     assert o.term_thres == pytest.approx(float(final_thres), rel=1e-12)
     assert range_err(got, g["nn00_solve"]) <= 1e-12
+
+
+def test_multigrid_driver_matches_reference(golden_multigrid):
+    """The oracle's restatement of inpaint_multigrid (fd_pde_inpainter.py:187-279) against the
+    reference fixtures: per-level grid sizes and update counts, the result, the write-through into
+    the caller's array and the final (mutated) threshold."""
+    import ast
+    g = golden_multigrid
+    mask = g["mask"]
+    for row in g["meta"]:
+        key, method, conv, dt, crit, thres, levels, min_res, init, per_level, final_thres = str(row).split("|")
+        opts = dict(METHOD_OPTS[method])
+        opts.update(convolver=conv, term_criteria=crit, term_thres=float(thres), term_check_iters=10,
+                    mgs_levels=int(levels), mgs_min_res=int(min_res), init_with=init, max_iters=20000)
+        o = OracleInpainter(method, **opts)
+        caller = g["image__" + dt].copy()
+        got = o.inpaint(caller, mask)
+        assert o.history == ast.literal_eval(per_level), (key, o.history)
+        ref = g[key]
+        assert got.dtype == ref.dtype
+        assert np.array_equal(got[mask], ref[mask]), key
+        assert range_err(got, ref) <= (1e-11 if dt == "f64" else 5e-6), (key, range_err(got, ref))
+        assert np.allclose(caller, g[key + "_caller_after"], rtol=0, atol=1e-9 if dt == "f64" else 1e-3), key
+        assert float(o.term_thres) == pytest.approx(float(final_thres), rel=1e-6), key
+
+
+def test_product_resize_equals_oracle_resize():
+    """The host tables the multigrid kernel consumes (product) and the oracle's cv2.resize restatement
+    are two independent statements of the same rule."""
+    from heightmap_interpolation_b200.inpainting.multigrid import resize_bilinear as product_resize
+    from oracle.fdpde_oracle import resize_bilinear as oracle_resize
+    rng = np.random.default_rng(5)
+    for dt in (np.float64, np.float32):
+        for (sr, sc), (dr, dc) in (((51, 66), (101, 131)), ((26, 33), (51, 66)), ((40, 40), (80, 80)),
+                                   ((7, 9), (13, 18))):
+            src = rng.standard_normal((sr, sc)).astype(dt)
+            assert np.array_equal(product_resize(src, dr, dc), oracle_resize(src, dr, dc))
