@@ -458,6 +458,31 @@ def test_multigrid_matches_reference(golden_multigrid):
         assert float(inp.term_thres) == pytest.approx(float(final_thres), rel=1e-6), key
 
 
+@pytest.mark.parametrize("method,dt,crit", [("harmonic", "f64", "absolute_percent"), ("ccst", "f32", "relative"),
+                                            ("tv", "f64", "relative")])
+def test_multigrid_matches_oracle_on_a_larger_grid(method, dt, crit):
+    """Levels chained on the device (up-sample + blend kernel, z-range from its reduction) against the
+    oracle's restatement of inpaint_multigrid on a 333 x 470 grid with odd sizes at every level and
+    large holes: same per-level update counts, filled cells within tolerance, same final threshold."""
+    import contextlib
+    import io
+    rows, cols = 333, 470
+    mask = synthetic.mask_holes((rows, cols), 12, 25, seed=4) & synthetic.mask_random((rows, cols), 0.2, seed=5)
+    img = synthetic.bathymetry((rows, cols), dtype=DTYPES[dt])
+    img[~mask] = 0
+    opts = dict(METHOD_OPTS[method], convolver="opencv", term_criteria=crit, term_thres=1e-5 if dt == "f64" else 1e-4,
+                term_check_iters=20, max_iters=3000, mgs_levels=3, mgs_min_res=50, init_with="mean")
+    inp = CLASSES[method](**opts)
+    ora = OracleInpainter(method, **opts)
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = inp.inpaint(img.copy(), mask)
+        ref = ora.inpaint(img.copy(), mask)
+    assert inp.history_ == ora.history and len(ora.history) == 3, (inp.history_, ora.history)
+    assert np.array_equal(got[mask], img[mask])
+    assert range_err(got, ref) <= TOL[dt], range_err(got, ref)
+    assert float(inp.term_thres) == pytest.approx(float(ora.term_thres), rel=1e-6)
+
+
 def test_multigrid_with_progress_output_equals_quiet_run(golden_multigrid):
     """print_progress drives the levels through the Python loop (progress table, same semantics) instead
     of hmi_run: same per-level iteration counts and bit-identical result."""
