@@ -378,6 +378,33 @@ def test_full_size_properties_4096():
     assert range_err(fast[-c:, -c:], ref[-c:, -c:]) <= 1e-12
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_large_odd_sized_grid_through_staged_copies(dt):
+    """A NumPy (pageable) grid large enough for the staged multi-threaded copies (csrc/hmi_xfer.cu) whose
+    width is not a multiple of the device pitch granularity: rows are re-pitched on the way in and out.
+    Round trip without sweeps is the identity; a few sweeps equal the generic kernel and, in a corner,
+    the oracle."""
+    rows, cols = 3001, 3011
+    mask = synthetic.mask_random((rows, cols), 0.3, seed=12)
+    img = synthetic.bathymetry((rows, cols), dtype=DTYPES[dt])
+    img[~mask] = 0
+    p = make_params(rows, cols, DTYPES[dt], METHODS["ccst"], orientation=1, dt=0.01, tension=0.3)
+    with Solver(p) as s:
+        s.set_problem_host(img, mask)
+        assert np.array_equal(s.get_result_host(), img)               # up and down again, bit for bit
+        out = np.full((rows, cols + 5), -1, dtype=DTYPES[dt])[:, :cols]    # a pitched host destination
+        C.check(s._lib.hmi_get_result_host(s._h, out.ctypes.data, out.strides[0]))
+        assert np.array_equal(out, img)
+    K = 4
+    fast, info = gpu_sweeps("ccst", "opencv", img, mask, K)
+    slow, _ = gpu_sweeps("ccst", "opencv", img, mask, K, kernel="generic")
+    assert info[0] == "stream" and np.array_equal(fast[mask], img[mask])
+    assert range_err(fast, slow) <= (1e-13 if dt == "f64" else 2e-6)
+    c, m = 64, 2 * K + 2
+    ref = oracle_sweeps("ccst", "opencv", img[-(c + m):, -(c + m):], mask[-(c + m):, -(c + m):], K)
+    assert range_err(fast[-c:, -c:], ref[-c:, -c:]) <= (1e-12 if dt == "f64" else 5e-6)
+
+
 def test_full_size_properties_16384_fp64_biharmonic():
     """BASELINE config 4 size (biharmonic = CCST tension 0, and harmonic; 16384^2 fp64, 40 % random
     mask, seed 2): known cells bit-exact, top-left and bottom-right corners equal the oracle, and a
