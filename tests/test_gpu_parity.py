@@ -415,8 +415,9 @@ def test_mid_sized_odd_grids_streaming_equals_generic(method, dt, conv):
         # fp64 agrees to 2.4e-11 on this grid, so the logic (borders, chunks, fused sweeps) is the same;
         # in fp32 the AMLE direction g/|g| is ill-conditioned where the gradient of 2500 m-offset data is
         # at rounding-noise level, and the two kernels (rsqrt + fma vs sqrt + divide) differ by up to
-        # 7.5e-3 of the range at isolated cells after 7 sweeps.  Recorded in DESIGN.md; the fp32 AMLE
-        # parity cases against the oracle are test_tv_amle_stream_kernel_matches_oracle.
+        # 7.5e-3 of the range at one cell after 7 sweeps — exactly what the CPU oracle in fp32 differs from
+        # the CPU oracle in fp64 by, at the same cell.  The fp32 AMLE parity cases
+        # against the oracle are test_tv_amle_stream_kernel_matches_oracle.
         pytest.skip("fp32 AMLE on data with kilometre-scale jumps is ill-conditioned (see comment)")
     rows, cols = 1501, 2047
     mask = synthetic.mask_holes((rows, cols), 30, 40, seed=3) & synthetic.mask_random((rows, cols), 0.3, seed=4)
