@@ -44,6 +44,11 @@ class HmiBlendInfo(ctypes.Structure):
                 ("has_nan", ctypes.c_int32), ("image_had_nan", ctypes.c_int32)]
 
 
+class HmiHaloInfo(ctypes.Structure):
+    _fields_ = [("block", ctypes.c_void_p), ("block_bytes", ctypes.c_uint64), ("device", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("ipc_handle", ctypes.c_ubyte * 64)]
+
+
 class HmiNorm(ctypes.Structure):
     _fields_ = [("sum_d2", ctypes.c_double), ("sum_f2", ctypes.c_double),
                 ("max_abs", ctypes.c_double), ("has_nan", ctypes.c_double)]
@@ -62,12 +67,37 @@ SYMBOLS = {
     "hmi_sweeps": (ctypes.c_int, [_vp, _i64, _vp]),
     "hmi_sweeps_overlap": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
     "hmi_sweeps_norm": (ctypes.c_int, [_vp, _i64, _vp, ctypes.POINTER(HmiNorm)]),
+    "hmi_halo_setup": (ctypes.c_int, [_vp, ctypes.POINTER(HmiHaloInfo)]),
+    "hmi_halo_connect": (ctypes.c_int, [_vp, ctypes.c_int32, _vp, ctypes.c_int32]),
+    "hmi_halo_connect_ipc": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_char_p]),
+    "hmi_sweeps_exchange": (ctypes.c_int, [_vp, _i64, _vp, _vp]),
+    "hmi_group_create": (ctypes.c_int, [ctypes.POINTER(HmiParams), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
+                                        ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "hmi_group_destroy": (None, [_vp]),
+    "hmi_group_set_problem_host": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz]),
+    "hmi_group_fill_unknown": (ctypes.c_int, [_vp, ctypes.c_double]),
+    "hmi_group_sweeps": (ctypes.c_int, [_vp, _i64]),
+    "hmi_group_sweeps_norm": (ctypes.c_int, [_vp, _i64, ctypes.POINTER(HmiNorm)]),
+    "hmi_group_run": (ctypes.c_int, [_vp, ctypes.POINTER(HmiStatus)]),
+    "hmi_group_set_term_thres": (ctypes.c_int, [_vp, ctypes.c_double]),
+    "hmi_group_get_result_host": (ctypes.c_int, [_vp, _vp, _sz]),
+    "hmi_group_sync": (ctypes.c_int, [_vp]),
+    "hmi_group_info": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_int32)]),
+    "hmi_group_slab": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_int32)]),
+    "hmi_group_launch_count": (_i64, [_vp]),
+    "hmi_inpaint_host_devices": (ctypes.c_int, [ctypes.POINTER(HmiParams), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
+                                                _vp, _vp, ctypes.c_int32, ctypes.c_double, _vp,
+                                                ctypes.POINTER(HmiStatus)]),
     "hmi_run": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(HmiStatus)]),
     "hmi_get_result_host": (ctypes.c_int, [_vp, _vp, _sz]),
     "hmi_get_result_device": (ctypes.c_int, [_vp, _vp, _sz, _vp]),
     "hmi_inpaint_host": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _vp, _vp,
                                         ctypes.POINTER(HmiStatus)]),
     "hmi_inpaint_host_fill": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _vp, ctypes.c_double, _vp,
+                                             ctypes.POINTER(HmiStatus)]),
+    "hmi_inpaint_host_init": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _vp, ctypes.c_double, _vp,
                                              ctypes.POINTER(HmiStatus)]),
     "hmi_set_problem_host_blend": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                   ctypes.c_int32, ctypes.POINTER(HmiBlendInfo)]),

@@ -8,15 +8,16 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
-#include "hmi_common.cuh"
+#include "hmi_internal.cuh"
 #include "hmi_stream.cuh"
 #include "hmi_stream_nl.cuh"
 #include "hmi_init.cuh"
 #include "hmi_xfer.cuh"
 
-namespace {
+namespace hmi {
 
 thread_local char g_err[512] = "";
 
@@ -29,25 +30,28 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                          \
-    do {                                                                                        \
-        cudaError_t e_ = (expr);                                                                \
-        if (e_ != cudaSuccess)                                                                  \
-            return fail(HMI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
-                        __FILE__, __LINE__);                                                    \
-    } while (0)
-
-long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
-
 // A small per-process cache of device allocations: the reference builds a fresh inpainter (and
 // fresh arrays) per work area (apps/interpolate_netcdf4.py:200), which on the device would mean a
 // cudaMalloc/cudaFree pair per 100+ MiB grid per call.  Freed blocks are kept (per device, exact
-// size match) up to a byte budget and handed back to the next solver.
+// size match) up to a byte budget and handed back to the next solver.  The budget is the smaller of
+// 24 GiB and a quarter of the device's memory, so that other allocators in the process (torch, NCCL)
+// are not starved; hmi_release_cache() returns everything to the driver.
 struct CachedBlock { int device; size_t bytes; void *ptr; };
 std::mutex g_cache_mu;
 std::vector<CachedBlock> g_cache;
 size_t g_cache_bytes = 0;
-const size_t kCacheBudget = (size_t)24 << 30;   // bytes kept at most
+size_t g_cache_budget = 0;                      // 0 = not sized yet
+
+static void drop_blocks(std::vector<CachedBlock> &drop)
+{
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (auto &b : drop) {
+        cudaSetDevice(b.device);
+        cudaFree(b.ptr);
+    }
+    cudaSetDevice(prev);
+}
 
 cudaError_t cached_malloc(int device, void **p, size_t bytes)
 {
@@ -70,11 +74,69 @@ cudaError_t cached_malloc(int device, void **p, size_t bytes)
             drop.swap(g_cache);
             g_cache_bytes = 0;
         }
-        for (auto &b : drop) cudaFree(b.ptr);
+        drop_blocks(drop);
         e = cudaMalloc(p, bytes);
     }
     return e;
 }
+
+void cached_free(int device, void *p, size_t bytes)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_cache_budget == 0) {
+            size_t free_b = 0, total_b = 0;
+            g_cache_budget = (size_t)24 << 30;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b / 4 < g_cache_budget) g_cache_budget = total_b / 4;
+            cudaGetLastError();
+        }
+        if (bytes >= ((size_t)1 << 20) && g_cache_bytes + bytes <= g_cache_budget && g_cache.size() < 64) {
+            g_cache.push_back({device, bytes, p});
+            g_cache_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+
+const DriverApi *driver_api()
+{
+    static DriverApi api;
+    static int state = 0;                       // 0 = not tried, 1 = ok, -1 = failed
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (state == 0) {
+        struct { const char *name; void **fn; } want[] = {
+            {"cuStreamWriteValue32", (void **)&api.streamWriteValue32},
+            {"cuStreamWaitValue32", (void **)&api.streamWaitValue32},
+            {"cuTensorMapEncodeTiled", (void **)&api.tensorMapEncodeTiled},
+        };
+        state = 1;
+        for (auto &w : want) {
+            cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+            const cudaError_t e = cudaGetDriverEntryPoint(w.name, w.fn, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*w.fn) {
+                cudaGetLastError();
+                fail(HMI_ERR_CUDA, "driver entry point %s is not available", w.name);
+                state = -1;
+                break;
+            }
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
+
+}  // namespace hmi
+
+using hmi::fail;
+using hmi::round_up;
+using hmi::cached_malloc;
+using hmi::cached_free;
+
+namespace {
+
+using hmi::g_cache_mu;
 
 std::vector<double *> g_pinned;                 // recycled 4-double pinned result buffers
 
@@ -102,20 +164,6 @@ void pinned_put(double *p)
 
 int g_cc_major[64] = {0};                       // compute capability major per device (0 = unknown)
 
-void cached_free(int device, void *p, size_t bytes)
-{
-    if (!p) return;
-    {
-        std::lock_guard<std::mutex> lk(g_cache_mu);
-        if (bytes >= ((size_t)1 << 20) && g_cache_bytes + bytes <= kCacheBudget && g_cache.size() < 64) {
-            g_cache.push_back({device, bytes, p});
-            g_cache_bytes += bytes;
-            return;
-        }
-    }
-    cudaFree(p);
-}
-
 // The streaming kernel packs four mask bytes with one multiply, which needs them to be exactly 0/1.
 __global__ void normalize_mask_kernel(uint8_t *m, size_t n)
 {
@@ -141,39 +189,10 @@ __global__ void fill_unknown_kernel(T *f, long long pitch, const uint8_t *m, lon
 
 }  // namespace
 
-struct hmi_solver {
-    hmi_params p;
-    int elem = 0;            // bytes per cell
-    int radius = 1;          // stencil radius of one sweep
-    long long pitch = 0;     // elements per row
-    long long mpitch = 0;    // bytes per mask row
-    int phys_rows = 0;       // ghost_top + rows + ghost_bottom
-    char *buf[2] = {nullptr, nullptr};
-    uint8_t *mask = nullptr;
-    int cur = 0;
-    void *d_scratch = nullptr;   // one block: partials | result | counter
-    size_t scratch_bytes = 0;
-    double *d_partials = nullptr;
-    unsigned int *d_counter = nullptr;
-    double *d_result = nullptr;
-    double *h_result = nullptr;  // pinned, recycled
-    int max_blocks = 0;
-    bool use_stream = false;
-    bool use_nl = false;     // streaming kernel for TV / AMLE
-    int tb = 1;              // sweeps fused per launch
-    int chunk_rows = 0;      // 0 = auto
-    int vec = 0;             // streaming kernel: cells per lane (0 = default)
-    int tma = 0;             // streaming kernel: TMA bulk-copy staging instead of cp.async
-    long long launches = 0;
-    bool has_problem = false;
-    size_t grid_bytes = 0, mask_bytes = 0;
-    cudaEvent_t ev = nullptr;   // main -> side stream dependency of hmi_sweeps_overlap
-};
-
-namespace {
+namespace hmi {
 
 template <typename T>
-int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip)
+static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip)
 {
     const hmi_params &p = s->p;
     // Over-relaxation (fd_pde_inpainter.py:317-318): fnew = f(1-w) + (f + dt step)w = f + (w dt) step for
@@ -247,32 +266,30 @@ int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t
     return HMI_OK;
 }
 
-int run_block(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip = true)
+int run_block(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip)
 {
     return s->p.dtype == HMI_F64 ? run_block_t<double>(s, k, lo, hi, do_norm, st, flip)
                                  : run_block_t<float>(s, k, lo, hi, do_norm, st, flip);
 }
 
-// n sweeps as a sequence of temporal blocks.  On a slab with ghost rows the halos must be fresh
-// on entry and n*radius must not exceed the ghost depth: block j also advances the ghost rows
-// that later blocks of this call still need (a shrinking trapezoid), so no exchange is needed
-// inside the call.
-int do_sweeps(hmi_solver *s, long long n, bool norm_on_last, cudaStream_t st)
+static int check_ghost_depth(const hmi_solver *s, long long n)
 {
     const hmi_params &p = s->p;
-    if (!s->has_problem) return fail(HMI_ERR_STATE, "hmi_set_problem_* has not been called");
-    if (n < 0) return fail(HMI_ERR_BAD_ARG, "negative sweep count");
-    const bool ghosts = p.ghost_top > 0 || p.ghost_bottom > 0;
-    if (ghosts) {
-        const long long need = n * s->radius;
-        if ((p.ghost_top > 0 && need > p.ghost_top) || (p.ghost_bottom > 0 && need > p.ghost_bottom))
-            return fail(HMI_ERR_BAD_ARG,
-                        "%lld sweeps of radius %d need %lld ghost rows, the slab has %d/%d", n,
-                        s->radius, need, p.ghost_top, p.ghost_bottom);
-    }
+    const long long need = n * s->radius;
+    if ((p.ghost_top > 0 && need > p.ghost_top) || (p.ghost_bottom > 0 && need > p.ghost_bottom))
+        return fail(HMI_ERR_BAD_ARG, "%lld sweeps of radius %d need %lld ghost rows, the slab has %d/%d", n,
+                    s->radius, need, p.ghost_top, p.ghost_bottom);
+    return HMI_OK;
+}
+
+// Blocks [done, upto) of an n-sweep call: block j also advances the ghost rows that later blocks of
+// the call still need (a shrinking trapezoid), so no exchange is needed inside the call.
+static int trapezoid_blocks(hmi_solver *s, long long n, long long upto, bool norm_on_last, cudaStream_t st)
+{
+    const hmi_params &p = s->p;
     long long done = 0;
-    while (done < n) {
-        long long k = n - done;
+    while (done < upto) {
+        long long k = upto - done;
         if (k > s->tb) k = s->tb;
         // the streaming kernel fuses the convergence sums into a single-sweep launch: keep the
         // last sweep of a check window on its own
@@ -281,21 +298,96 @@ int do_sweeps(hmi_solver *s, long long n, bool norm_on_last, cudaStream_t st)
         const int lo = p.ghost_top > 0 ? (int)(-after * s->radius) : 0;
         const int hi = p.rows + (p.ghost_bottom > 0 ? (int)(after * s->radius) : 0);
         const bool last = (done + k == n);
-        const int rc = run_block(s, (int)k, lo, hi, norm_on_last && last, st);
+        const int rc = run_block(s, (int)k, lo, hi, norm_on_last && last, st, true);
         if (rc != HMI_OK) return rc;
         done += k;
     }
     return HMI_OK;
 }
 
+// Work queued on a side stream by an earlier call (edge rows, halo pushes) must be finished before
+// `st` touches the grids again.
+static int join_side(hmi_solver *s, cudaStream_t st)
+{
+    if (s->side_pending && s->ev_side) CUDA_TRY(cudaStreamWaitEvent(st, s->ev_side, 0));
+    s->side_pending = false;
+    return HMI_OK;
+}
+
+// n sweeps as a sequence of temporal blocks.  On a slab with ghost rows the halos must be fresh
+// on entry and n*radius must not exceed the ghost depth.
+int do_sweeps(hmi_solver *s, long long n, bool norm_on_last, cudaStream_t st)
+{
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "hmi_set_problem_* has not been called");
+    if (n < 0) return fail(HMI_ERR_BAD_ARG, "negative sweep count");
+    int rc = check_ghost_depth(s, n);
+    if (rc != HMI_OK) return rc;
+    if ((rc = join_side(s, st)) != HMI_OK) return rc;
+    s->last_main = st;
+    if (n == 0) return HMI_OK;
+    // linked slabs (hmi_halo_*): bring the ghost rows up to date first; afterwards they are stale
+    if (s->linked && (rc = halo_ensure_fresh(s, st)) != HMI_OK) return rc;
+    rc = trapezoid_blocks(s, n, n, norm_on_last, st);
+    if (s->linked) s->halo_state = 2;
+    return rc;
+}
+
+// n sweeps with the last temporal block split: the rows the neighbouring slabs need (the first
+// ghost_top and last ghost_bottom interior rows) are produced first, on the side stream, and the
+// interior on the main stream.  On return ev_side has been recorded on `ss` behind the edge launches;
+// callers queue the halo transfer on `ss` and record ev_side again.
+int do_sweeps_split(hmi_solver *s, long long n, cudaStream_t ms, cudaStream_t ss)
+{
+    const hmi_params &p = s->p;
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "hmi_set_problem_* has not been called");
+    if (n < 1) return fail(HMI_ERR_BAD_ARG, "the split sweep call needs n >= 1");
+    int rc = check_ghost_depth(s, n);
+    if (rc != HMI_OK) return rc;
+    if ((rc = join_side(s, ms)) != HMI_OK) return rc;
+    const int bt = p.ghost_top, bb = p.ghost_bottom;     // rows each neighbour needs from this slab
+    if (!s->ev) CUDA_TRY(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
+    if (!s->ev_side) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_side, cudaEventDisableTiming));
+    s->last_main = ms;
+    s->last_side = ss;
+    if ((bt == 0 && bb == 0) || p.rows - bt - bb < 8 || ss == ms) {
+        // nothing to overlap with: everything on the main stream; the side stream still has to see it
+        if ((rc = trapezoid_blocks(s, n, n, false, ms)) != HMI_OK) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev, ms));
+        CUDA_TRY(cudaStreamWaitEvent(ss, s->ev, 0));
+        CUDA_TRY(cudaEventRecord(s->ev_side, ss));
+        s->side_pending = (ss != ms);
+        return HMI_OK;
+    }
+    long long k_last = n % s->tb == 0 ? s->tb : n % s->tb;
+    if (k_last > n) k_last = n;
+    // all blocks but the last: the shrinking trapezoid, on the main stream
+    if ((rc = trapezoid_blocks(s, n, n - k_last, false, ms)) != HMI_OK) return rc;
+    // last block: the rows the neighbours are waiting for go first, on the side stream; the
+    // interior follows on the main stream
+    CUDA_TRY(cudaEventRecord(s->ev, ms));
+    CUDA_TRY(cudaStreamWaitEvent(ss, s->ev, 0));
+    if (bt > 0) rc = run_block(s, (int)k_last, 0, bt, false, ss, false);
+    if (rc == HMI_OK && bb > 0) rc = run_block(s, (int)k_last, p.rows - bb, p.rows, false, ss, false);
+    if (rc == HMI_OK) rc = run_block(s, (int)k_last, bt, p.rows - bb, false, ms, true);
+    if (rc != HMI_OK) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev_side, ss));
+    s->side_pending = true;
+    return HMI_OK;
+}
+
 int fetch_norm(hmi_solver *s, cudaStream_t st, hmi_norm *out)
 {
-    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // result[0..3] and the device error word behind the counter travel in one copy
+    CUDA_TRY(cudaMemcpyAsync(s->h_result, s->d_result, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     out->sum_d2 = s->h_result[0];
     out->sum_f2 = s->h_result[1];
     out->max_abs = s->h_result[2];
     out->has_nan = s->h_result[3];
+    const unsigned int *w = reinterpret_cast<const unsigned int *>(s->h_result + 4);
+    if (w[2] != 0u)
+        return fail(HMI_ERR_CUDA, "halo exchange timed out: a neighbouring slab did not deliver its rows "
+                                  "(device error word %u)", w[2]);
     return HMI_OK;
 }
 
@@ -305,27 +397,78 @@ double norm_to_diff(const hmi_params &p, const hmi_norm &n)
     return n.has_nan != 0.0 ? nan("") : n.max_abs;
 }
 
+cudaStream_t pick_stream(hmi_solver *, void *stream) { return (cudaStream_t)stream; }
+
+int sync_solver(hmi_solver *s)
+{
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    CUDA_TRY(cudaStreamSynchronize(s->last_main));        // NULL = the legacy default stream
+    if (s->last_side) CUDA_TRY(cudaStreamSynchronize(s->last_side));
+    if (s->own) CUDA_TRY(cudaStreamSynchronize(s->own));
+    if (s->own_side) CUDA_TRY(cudaStreamSynchronize(s->own_side));
+    s->side_pending = false;
+    return HMI_OK;
+}
+
+}  // namespace hmi
+
+namespace {
+
 void destroy(hmi_solver *s)
 {
     if (!s) return;
     cudaSetDevice(s->p.device);
-    cudaDeviceSynchronize();                     // nothing may still be using the blocks we recycle
+    hmi::sync_solver(s);                         // nothing may still be using the blocks we recycle
+    cudaGetLastError();
+    hmi::halo_release(s);
     cached_free(s->p.device, s->buf[0], s->grid_bytes);
     cached_free(s->p.device, s->buf[1], s->grid_bytes);
     cached_free(s->p.device, s->mask, s->mask_bytes);
     cached_free(s->p.device, s->d_scratch, s->scratch_bytes);
     pinned_put(s->h_result);
     if (s->ev) cudaEventDestroy(s->ev);
+    if (s->ev_side) cudaEventDestroy(s->ev_side);
+    if (s->own) cudaStreamDestroy(s->own);
+    if (s->own_side) cudaStreamDestroy(s->own_side);
+    delete[] s->tmaps;
     delete s;
 }
 
 }  // namespace
 
+namespace hmi {
+
+// 'zeros' / 'mean' initialiser on the device copy (both ghost and interior rows), on the solver's stream
+int fill_unknown(hmi_solver *s, double value)
+{
+    if (!s->has_problem) return fail(HMI_ERR_STATE, "no problem loaded");
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    const dim3 grid((s->p.cols + 255) / 256, s->phys_rows < 1024 ? s->phys_rows : 1024);
+    char *f = s->buf[s->cur];
+    if (s->p.dtype == HMI_F64)
+        fill_unknown_kernel<double><<<grid, 256, 0, s->own>>>((double *)f, s->pitch, s->mask, s->mpitch, s->phys_rows,
+                                                              s->p.cols, value);
+    else
+        fill_unknown_kernel<float><<<grid, 256, 0, s->own>>>((float *)f, s->pitch, s->mask, s->mpitch, s->phys_rows,
+                                                             s->p.cols, (float)value);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(HMI_ERR_CUDA, "fill kernel launch failed: %s", cudaGetErrorString(e));
+    s->last_main = s->own;
+    return HMI_OK;
+}
+
+}  // namespace hmi
+
+using hmi::do_sweeps;
+using hmi::fetch_norm;
+using hmi::norm_to_diff;
+using hmi::run_block;
+
 extern "C" {
 
 int hmi_abi_version(void) { return HMI_ABI_VERSION; }
 
-const char *hmi_last_error(void) { return g_err; }
+const char *hmi_last_error(void) { return hmi::g_err; }
 
 int hmi_device_count(void)
 {
@@ -455,13 +598,19 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
             s->d_partials = (double *)s->d_scratch;
             s->d_result = (double *)((char *)s->d_scratch + part);
             s->d_counter = (unsigned int *)((char *)s->d_scratch + part + 4 * sizeof(double));
+            s->d_error = s->d_counter + 2;
         }
         s->h_result = pinned_get();
         if (!s->h_result) { e = cudaErrorMemoryAllocation; break; }
-        if ((e = cudaMemsetAsync(s->buf[0], 0, grid_bytes)) != cudaSuccess) break;
-        if ((e = cudaMemsetAsync(s->buf[1], 0, grid_bytes)) != cudaSuccess) break;
-        if ((e = cudaMemsetAsync(s->mask, 1, mask_bytes)) != cudaSuccess) break;
-        if ((e = cudaMemsetAsync(s->d_result, 0, 4 * sizeof(double) + sizeof(unsigned int))) != cudaSuccess) break;
+        // the solver's own streams: uploads / downloads / one-shot solves never touch the legacy
+        // default stream, so several solvers (threads, GPUs) do not serialise on it
+        if ((e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->buf[0], 0, grid_bytes, s->own)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->buf[1], 0, grid_bytes, s->own)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->mask, 1, mask_bytes, s->own)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(s->d_result, 0, 6 * sizeof(double), s->own)) != cudaSuccess) break;
+        // callers may continue on any (non-blocking) stream: the zero fill must not land later
+        if ((e = cudaStreamSynchronize(s->own)) != cudaSuccess) break;
     } while (0);
     if (e != cudaSuccess) {
         rc = fail(HMI_ERR_CUDA, "device allocation failed (%zu bytes per grid): %s", grid_bytes, cudaGetErrorString(e));
@@ -485,7 +634,9 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
         return HMI_OK;
     }
     if (!strcmp(key, "tma")) {
-        s->tma = value ? 1 : 0;
+        // 0 = cp.async ring (default), 1 = 1-D bulk copies per row, 2 = 2-D tensor-map boxes (interior strips)
+        if (value < 0 || value > 2) return fail(HMI_ERR_BAD_ARG, "tma must be 0, 1 or 2");
+        s->tma = (int)value;
         return HMI_OK;
     }
     if (!strcmp(key, "vec")) {
@@ -523,14 +674,17 @@ int hmi_set_problem_host(hmi_solver *s, const void *image, size_t image_pitch_by
     s->cur = 0;
     // pinned memory: straight DMA (one linear copy when dense); pageable memory (NumPy arrays): staged
     // through pinned ring buffers by several host threads (hmi_xfer.cu)
+    int rc = hmi::sync_solver(s);                // earlier sweeps may still be reading the grids
+    if (rc != HMI_OK) return rc;
     CUDA_TRY(hmi::copy_h2d_2d(s->p.device, s->buf[0], (size_t)s->pitch * s->elem, image, image_pitch_bytes, wbytes,
-                              s->phys_rows));
+                              s->phys_rows, s->own));
     CUDA_TRY(hmi::copy_h2d_2d(s->p.device, s->mask, (size_t)s->mpitch, mask, mask_pitch_bytes, (size_t)s->p.cols,
-                              s->phys_rows));
-    normalize_mask_kernel<<<592, 256>>>(s->mask, (size_t)s->phys_rows * s->mpitch);
+                              s->phys_rows, s->own));
+    normalize_mask_kernel<<<592, 256, 0, s->own>>>(s->mask, (size_t)s->phys_rows * s->mpitch);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(nullptr));    // the caller may reuse its host buffers on return
+    CUDA_TRY(cudaStreamSynchronize(s->own));     // the caller may reuse its host buffers on return
     s->has_problem = true;
+    s->halo_state = 0;                           // slabs are loaded with their neighbours' rows
     return HMI_OK;
 }
 
@@ -544,6 +698,8 @@ int hmi_set_problem_device(hmi_solver *s, const void *image_dev, size_t image_pi
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(s->p.device));
     s->cur = 0;
+    s->last_main = st;
+    s->halo_state = 0;
     CUDA_TRY(cudaMemcpy2DAsync(s->buf[0], (size_t)s->pitch * s->elem, image_dev, image_pitch_bytes,
                                wbytes, s->phys_rows, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpy2DAsync(s->mask, (size_t)s->mpitch, mask_dev, mask_pitch_bytes,
@@ -564,39 +720,12 @@ int hmi_sweeps(hmi_solver *s, int64_t n, void *stream)
 int hmi_sweeps_overlap(hmi_solver *s, int64_t n, void *main_stream, void *side_stream)
 {
     if (!s) return fail(HMI_ERR_BAD_ARG, "null solver");
-    const hmi_params &p = s->p;
     if (n < 1) return fail(HMI_ERR_BAD_ARG, "hmi_sweeps_overlap needs n >= 1");
-    CUDA_TRY(cudaSetDevice(p.device));
-    cudaStream_t ms = (cudaStream_t)main_stream, ss = (cudaStream_t)side_stream;
-    const int bt = p.ghost_top, bb = p.ghost_bottom;     // rows each neighbour needs from this slab
-    if ((bt == 0 && bb == 0) || p.rows - bt - bb < 8 || ss == ms)
-        return do_sweeps(s, n, false, ms);               // nothing to overlap with
-    long long k_last = n % s->tb == 0 ? s->tb : n % s->tb;
-    if (k_last > n) k_last = n;
-    const long long first = n - k_last;
-    if (n * s->radius > (bt > 0 ? bt : n * s->radius) || n * s->radius > (bb > 0 ? bb : n * s->radius))
-        return fail(HMI_ERR_BAD_ARG, "%lld sweeps need more ghost rows than the slab has", (long long)n);
-    // all blocks but the last: the shrinking trapezoid, on the main stream
-    long long done = 0;
-    while (done < first) {
-        long long k = first - done;
-        if (k > s->tb) k = s->tb;
-        const long long after = n - (done + k);
-        const int lo = bt > 0 ? (int)(-after * s->radius) : 0;
-        const int hi = p.rows + (bb > 0 ? (int)(after * s->radius) : 0);
-        const int rc = run_block(s, (int)k, lo, hi, false, ms);
-        if (rc != HMI_OK) return rc;
-        done += k;
-    }
-    // last block: the rows the neighbours are waiting for go first, on the side stream (the caller
-    // starts the halo exchange behind them); the interior follows on the main stream
-    if (!s->ev) CUDA_TRY(cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(s->ev, ms));
-    CUDA_TRY(cudaStreamWaitEvent(ss, s->ev, 0));
-    int rc = HMI_OK;
-    if (bt > 0) rc = run_block(s, (int)k_last, 0, bt, false, ss, false);
-    if (rc == HMI_OK && bb > 0) rc = run_block(s, (int)k_last, p.rows - bb, p.rows, false, ss, false);
-    if (rc == HMI_OK) rc = run_block(s, (int)k_last, bt, p.rows - bb, false, ms, true);
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    // on every path the side stream ends up ordered behind the rows the neighbours need, so the
+    // caller's exchange on it never sends rows that are still being computed
+    const int rc = hmi::do_sweeps_split(s, n, (cudaStream_t)main_stream, (cudaStream_t)side_stream);
+    s->side_pending = false;     // this entry point leaves joining the two streams to the caller
     return rc;
 }
 
@@ -615,38 +744,16 @@ int hmi_run(hmi_solver *s, void *stream, hmi_status *status)
     if (!s || !status) return fail(HMI_ERR_BAD_ARG, "null argument");
     const hmi_params &p = s->p;
     if (p.ghost_top || p.ghost_bottom)
-        return fail(HMI_ERR_STATE, "hmi_run drives a whole grid; slabs are driven by the host layer");
+        return fail(HMI_ERR_STATE, "hmi_run drives a whole grid; slabs are driven by hmi_group_run or the host layer");
     if (!s->has_problem) return fail(HMI_ERR_STATE, "hmi_set_problem_* has not been called");
     CUDA_TRY(cudaSetDevice(p.device));
     cudaStream_t st = (cudaStream_t)stream;
-    const long long T = p.term_check_iters, maxit = p.max_iters;
-    long long i = 0;
-    status->updates_done = 0;
-    status->last_diff = 100000.0;  // fd_pde_inpainter.py:309
-    status->converged = 0;
-    status->checks = 0;
-    while (i < maxit) {
-        const long long c = (i + T - 1) / T * T;  // next iteration index with c % T == 0
-        if (c >= maxit) {                         // no check left before max_iters
-            const int rc = do_sweeps(s, maxit - i, false, st);
-            if (rc != HMI_OK) return rc;
-            i = maxit;
-            break;
-        }
-        hmi_norm nm;
-        int rc = do_sweeps(s, c - i + 1, true, st);
-        if (rc != HMI_OK) return rc;
-        rc = fetch_norm(s, st, &nm);
-        if (rc != HMI_OK) return rc;
-        i = c + 1;
-        status->checks += 1;
-        status->last_diff = norm_to_diff(p, nm);
-        if (status->last_diff < p.term_thres) {   // NaN compares false: never terminates on NaN
-            status->converged = 1;
-            break;
-        }
-    }
-    status->updates_done = i;
+    const int rc = hmi::reference_loop(p, [&](long long n, bool norm, hmi_norm *nm) {
+        int r = do_sweeps(s, n, norm, st);
+        if (r == HMI_OK && norm) r = fetch_norm(s, st, nm);
+        return r;
+    }, status);
+    if (rc != HMI_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
     return HMI_OK;
 }
@@ -657,10 +764,11 @@ int hmi_get_result_host(hmi_solver *s, void *out, size_t out_pitch_bytes)
     if (!s->has_problem) return fail(HMI_ERR_STATE, "no problem loaded");
     const size_t wbytes = (size_t)s->p.cols * s->elem;
     if (out_pitch_bytes < wbytes) return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
-    CUDA_TRY(cudaSetDevice(s->p.device));
-    CUDA_TRY(cudaDeviceSynchronize());
+    const int rc = hmi::sync_solver(s);
+    if (rc != HMI_OK) return rc;
     const char *src = s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
-    CUDA_TRY(hmi::copy_d2h_2d(s->p.device, out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows));
+    CUDA_TRY(hmi::copy_d2h_2d(s->p.device, out, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes, s->p.rows,
+                              s->own));
     return HMI_OK;
 }
 
@@ -671,13 +779,17 @@ int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, 
     const size_t wbytes = (size_t)s->p.cols * s->elem;
     if (out_pitch_bytes < wbytes) return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
     CUDA_TRY(cudaSetDevice(s->p.device));
+    if (s->side_pending && s->ev_side) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_side, 0));
     const char *src = s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
     CUDA_TRY(cudaMemcpy2DAsync(out_dev, out_pitch_bytes, src, (size_t)s->pitch * s->elem, wbytes,
                                s->p.rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return HMI_OK;
 }
 
-static int inpaint_host_impl(const hmi_params *params, const void *image, const uint8_t *mask, bool fill,
+// fill: 0 = the grid is already initialised; 1 = unknown cells of the device copy <- fill_value;
+// 2 = as 1 and the caller's host array is initialised in place too (what the reference's Initializer
+// does first, initializer.py:15-18) — after the upload has read it, while the device solves.
+static int inpaint_host_impl(const hmi_params *params, const void *image, const uint8_t *mask, int fill,
                              double fill_value, void *out, hmi_status *status)
 {
     if (!params || !image || !mask || !out || !status) return fail(HMI_ERR_BAD_ARG, "null argument");
@@ -686,19 +798,14 @@ static int inpaint_host_impl(const hmi_params *params, const void *image, const 
     if (rc != HMI_OK) return rc;
     const size_t elem = params->dtype == HMI_F64 ? 8 : 4;
     rc = hmi_set_problem_host(s, image, (size_t)params->cols * elem, mask, (size_t)params->cols);
-    if (rc == HMI_OK && fill) {
-        const dim3 grid((params->cols + 255) / 256, s->phys_rows < 1024 ? s->phys_rows : 1024);
-        if (params->dtype == HMI_F64)
-            fill_unknown_kernel<double><<<grid, 256>>>((double *)s->buf[0], s->pitch, s->mask, s->mpitch, s->phys_rows,
-                                                       params->cols, fill_value);
-        else
-            fill_unknown_kernel<float><<<grid, 256>>>((float *)s->buf[0], s->pitch, s->mask, s->mpitch, s->phys_rows,
-                                                      params->cols, (float)fill_value);
-        const cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = fail(HMI_ERR_CUDA, "fill kernel launch failed: %s", cudaGetErrorString(e));
-    }
-    if (rc == HMI_OK) rc = hmi_run(s, nullptr, status);
+    std::thread host_init;
+    if (rc == HMI_OK && fill == 2)
+        host_init = std::thread(hmi_host_fill_unknown, const_cast<void *>(image), mask,
+                                (int64_t)params->rows * params->cols, params->dtype, fill_value);
+    if (rc == HMI_OK && fill) rc = hmi::fill_unknown(s, fill_value);
+    if (rc == HMI_OK) rc = hmi_run(s, s->own, status);
     if (rc == HMI_OK) rc = hmi_get_result_host(s, out, (size_t)params->cols * elem);
+    if (host_init.joinable()) host_init.join();
     hmi_destroy(s);
     return rc;
 }
@@ -706,13 +813,19 @@ static int inpaint_host_impl(const hmi_params *params, const void *image, const 
 int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
                      hmi_status *status)
 {
-    return inpaint_host_impl(params, image, mask, false, 0.0, out, status);
+    return inpaint_host_impl(params, image, mask, 0, 0.0, out, status);
 }
 
 int hmi_inpaint_host_fill(const hmi_params *params, const void *image, const uint8_t *mask, double fill_value,
                           void *out, hmi_status *status)
 {
-    return inpaint_host_impl(params, image, mask, true, fill_value, out, status);
+    return inpaint_host_impl(params, image, mask, 1, fill_value, out, status);
+}
+
+int hmi_inpaint_host_init(const hmi_params *params, void *image, const uint8_t *mask, double fill_value, void *out,
+                          hmi_status *status)
+{
+    return inpaint_host_impl(params, image, mask, 2, fill_value, out, status);
 }
 
 int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *mask, size_t mask_pitch_bytes,
@@ -878,19 +991,13 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes)
 
 int hmi_release_cache(void)
 {
-    std::vector<CachedBlock> drop;
+    std::vector<hmi::CachedBlock> drop;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        drop.swap(g_cache);
-        g_cache_bytes = 0;
+        drop.swap(hmi::g_cache);
+        hmi::g_cache_bytes = 0;
     }
-    int prev = 0;
-    cudaGetDevice(&prev);
-    for (auto &b : drop) {
-        cudaSetDevice(b.device);
-        cudaFree(b.ptr);
-    }
-    cudaSetDevice(prev);
+    hmi::drop_blocks(drop);
     return HMI_OK;
 }
 

@@ -4,15 +4,21 @@ The reference is a single process holding the whole grid; this m
 parallelism the path admits: every sweep is a local stencil, so the grid is cut into contiguous row
 slabs, each slab carries `ghost` rows of its neighbours above and below, and
 
-  * every `exchange_every` sweeps the ghost rows are refreshed with one grouped send/recv per
-    neighbour (NCCL over NVLink; gloo in the CPU tests).  Between exchanges the solver advances a
+  * every `exchange_every` sweeps the ghost rows are refreshed.  On the GPUs this is the peer-memory
+    halo link of csrc/hmi_halo.cu (`halo="peer"`, the default): the slab's copy engine pushes its
+    rows next to a seam into a staging area in the neighbour's HBM (mapped through CUDA IPC, the
+    64-byte handles are all-gathered once at set-up) and publishes a flag there; no SM and no
+    collective are involved, and the push overlaps the interior update of the same temporal block.
+    `halo="nccl"` keeps the grouped send/recv per neighbour of round 1 as the comparison baseline;
+    the CPU tests (gloo) use the same send/recv path.  Between exchanges the solver advances a
     shrinking trapezoid of ghost rows itself (see hmi_sweeps in include/hmi_b200.h), so
     ghost = radius * exchange_every rows buy `exchange_every` sweeps per exchange;
-  * on a check iteration the per-slab convergence sums are all-reduced (sum, sum, max, max) — the
-    only global quantity of the loop (fd_pde_inpainter.py:368-379);
+  * on a check iteration the per-slab convergence sums are all-reduced (sum, sum, max, max; NCCL) —
+    the only global quantity of the loop (fd_pde_inpainter.py:368-379);
   * the reflect-101 / zero border rule applies only at the global top and bottom, never at seams.
 
-`torch.distributed` is plumbing only: it moves ghost rows and four doubles.
+`torch.distributed` is plumbing only: it moves 64-byte handles and four doubles (and, with
+`halo="nccl"`, the ghost rows).
 """
 import numpy as np
 import torch
@@ -46,7 +52,9 @@ class _DevArray:
 class CudaSlabEngine:
     """The CUDA solver of one slab plus zero-copy torch views of its ghost/edge rows."""
 
-    def __init__(self, params):
+    def __init__(self, params, halo="peer"):
+        if halo not in ("peer", "nccl"):
+            raise ValueError("halo must be 'peer' or 'nccl'")
         self.solver = Solver(params)
         self.params = params
         self.device = torch.device("cuda", params.device)
@@ -54,6 +62,32 @@ class CudaSlabEngine:
         self.elem = 8 if params.dtype == C.HMI_F64 else 4
         self._views = {}            # device pointer -> torch view (the solver ping-pongs two grids)
         self._side = None           # side stream of the overlapped exchange
+        self.halo = halo
+        self.linked = False
+        self._group = None
+
+    def link(self, rank, world, group=None):
+        """Connect this slab to its neighbours' halo blocks (CUDA IPC): one all-gather of the 64-byte
+        handles, then cudaIpcOpenMemHandle of the rank above and below."""
+        if self.halo != "peer" or world == 1 or (self.params.ghost_top == 0 and self.params.ghost_bottom == 0):
+            return
+        info = self.solver.halo_setup()
+        mine = torch.tensor(list(bytes(info.ipc_handle)), dtype=torch.uint8, device=self.device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        if rank > 0:
+            self.solver.halo_connect_ipc(0, bytes(handles[rank - 1].cpu().tolist()))
+        if rank < world - 1:
+            self.solver.halo_connect_ipc(1, bytes(handles[rank + 1].cpu().tolist()))
+        dist.barrier(group=group)      # every block is mapped before anybody pushes
+        self.linked = True
+        self._group = group
+
+    def sweeps_exchange(self, n):
+        """n sweeps, then the push of the rows next to the seams into the neighbours' HBM, overlapped
+        with the interior update (hmi_sweeps_exchange)."""
+        main = torch.cuda.current_stream(self.device)
+        self.solver.sweeps_exchange(n, main.cuda_stream, 0)
 
     def load(self, image, mask):
         self.solver.set_problem_host(image, mask)
@@ -93,6 +127,10 @@ class CudaSlabEngine:
         return self.solver.get_result_host()
 
     def close(self):
+        if self.linked:                # nobody may still be pushing into a block about to be freed
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self._group)
+            self.linked = False
         self.solver.close()
 
 
@@ -113,6 +151,8 @@ class SlabSolver:
         self.exchanges = 0
         self.halo_fresh = True      # slabs are loaded with their neighbours' rows
         self.overlap = hasattr(engine, "sweeps_overlap")
+        # peer-memory halo links: the library tracks the freshness of the ghost rows itself
+        self.peer = bool(getattr(engine, "linked", False))
 
     # -- halo exchange: my first/last `g` interior rows -> the neighbour's ghost rows
     def exchange(self):
@@ -147,6 +187,10 @@ class SlabSolver:
         """k <= exchange_every sweeps.  Halos are refreshed before the block if they are stale;
         engines that can split their last launch refresh them again *after* it, overlapped with
         the interior update, so the next block starts without waiting."""
+        if self.peer:
+            self.engine.sweeps_exchange(k)
+            self.exchanges += 1
+            return
         if not self.halo_fresh:
             self.exchange()
         if self.overlap and self.world > 1:
@@ -165,7 +209,7 @@ class SlabSolver:
         blocks = list(self._blocks(n))
         for k in blocks[:-1]:
             self._block(k)
-        if not self.halo_fresh:
+        if not self.halo_fresh and not self.peer:
             self.exchange()
         nm = self.engine.sweeps_norm(blocks[-1])
         self.halo_fresh = False
@@ -195,7 +239,8 @@ def slab_rows_needed(rows, world, rank, radius, exchange_every):
 
 
 def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=None,
-                 engine_factory=None, group=None, global_rows=None, first_row=0, post_hook=None):
+                 engine_factory=None, group=None, global_rows=None, first_row=0, post_hook=None, halo="peer",
+                 out=None):
     """Distributed `inpaint_grid`: every rank passes the same global `image`/`mask` (already
     initialised, host arrays), or — so that no process ever holds the whole grid — only the rows
     [first_row, first_row + len(image)) of a grid of `global_rows` rows, which must cover this
@@ -239,10 +284,12 @@ def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=N
         lo = r0 - gt
     params = inpainter._make_params(r1 - r0, cols, image.dtype, ghost_top=gt, ghost_bottom=gb,
                                     device=device)
-    engine = (engine_factory or CudaSlabEngine)(params)
+    engine = engine_factory(params) if engine_factory else CudaSlabEngine(params, halo=halo)
     try:
         engine.load(np.ascontiguousarray(image[lo:lo + gt + (r1 - r0) + gb]),
                     np.ascontiguousarray(mask[lo:lo + gt + (r1 - r0) + gb]))
+        if hasattr(engine, "link"):
+            engine.link(rank, world, group)
         slab = SlabSolver(engine, rank, world, radius, gt, gb, exchange_every, r1 - r0, group)
         quiet = inpainter.print_progress and rank != 0
         if quiet:
@@ -256,7 +303,7 @@ def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=N
         inpainter.exchanges_ = slab.exchanges
         if not conv and rank == 0:
             print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
-        result = engine.result()
+        result = engine.result() if out is None else engine.solver.get_result_host(out)
         if post_hook is not None:
             post_hook(slab)
         return result, (r0, r1)

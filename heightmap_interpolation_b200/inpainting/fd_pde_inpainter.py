@@ -7,18 +7,19 @@ same constructor keywords, defaults and ``ValueError`` messages (:71-100), ``get
 convergence norm — runs in hand-written CUDA kernels behind the C ABI of ``include/hmi_b200.h``.
 
 Extra keywords (ignored by the reference, which silently drops unknown keys):
-``device`` (CUDA ordinal), ``kernel`` ("auto" | "generic" | "stream"), ``temporal_block`` (sweeps fused
-per launch, 0 = auto), ``nearest_backend`` ("b200" | "scipy": who evaluates ``init_with="nearest"``).  After a solve the object exposes ``iterations_``, ``last_diff_`` and
+``device`` (CUDA ordinal), ``devices`` (list of ordinals or "all": the grid is cut into row slabs over
+these GPUs of this process, include/hmi_b200.h hmi_group_*), ``kernel`` ("auto" | "generic" | "stream"),
+``temporal_block`` (sweeps fused per launch, 0 = auto), ``nearest_backend`` ("b200" | "scipy": who
+evaluates ``init_with="nearest"``).  After a solve the object exposes ``iterations_``, ``last_diff_`` and
 ``converged_`` (the reference only prints them).
 """
-import math
 from abc import ABC
 from timeit import default_timer as timer
 
 import numpy as np
 
 from .. import _capi as C
-from ..solver import Norm, Solver, inpaint_host, make_params
+from ..solver import Group, Norm, Solver, inpaint_host, inpaint_host_devices, make_params
 from .convolver import Convolver
 from .initializer import Initializer
 
@@ -50,6 +51,7 @@ class FDPDEInpainter(ABC):
         self.ts = 0
         # --- B200 back-end keywords
         self.device = kwargs.pop("device", None)
+        self.devices = kwargs.pop("devices", None)
         self.kernel = kwargs.pop("kernel", "auto")
         self.temporal_block = int(kwargs.pop("temporal_block", 0))
 
@@ -103,23 +105,25 @@ class FDPDEInpainter(ABC):
                 "convolver": self.convolver_type}
 
     def set_term_criteria(self, f):
-        """fd_pde_inpainter.py:141-158, including the in-place scaling of term_thres."""
-        self.term_criteria_int = self.map_term_criteria_str_to_int.get(self.term_criteria, -1)
-        if self.term_criteria_int == 0:
-            self.print_msg("* Termination criteria --> relative change = {:f}".format(self.term_thres))
-        elif self.term_criteria_int == 1:
-            self.print_msg("* Termination criteria --> absolute change = {:f}".format(self.term_thres))
-        elif self.term_criteria_int == 2:
-            max_val = np.max(f)
-            min_val = np.min(f)
-            z_range = abs(max_val - min_val)
-            self.print_msg("* Termination criteria --> absolute percent change:")
-            self.print_msg(f"    - Abs. Z range: {z_range:f}")
-            self.print_msg(f"    - Percent = {self.term_thres:f}")
-            self.term_thres = z_range * self.term_thres
-            self.print_msg(f"    - Terminate if absolute change < {self.term_thres:f}")
-        else:
+        """What fd_pde_inpainter.py:141-158 does: resolve the criterion name and, for 'absolute_percent',
+        turn the percentage into an absolute threshold using the z-range of the initialised grid `f` —
+        in place on the object, so a second solve with the same inpainter compounds it."""
+        kind = self.map_term_criteria_str_to_int.get(self.term_criteria, -1)
+        self.term_criteria_int = kind
+        if kind not in (0, 1, 2):
             raise ValueError("Unknown termination criteria!")
+        if kind < 2:
+            self.print_msg("* Termination criteria --> {:s} change = {:f}".format(("relative", "absolute")[kind],
+                                                                                 self.term_thres))
+            return
+        z_range = abs(np.max(f) - np.min(f))
+        percent = self.term_thres
+        self.term_thres = z_range * percent
+        for line in ("* Termination criteria --> absolute percent change:",
+                     f"    - Abs. Z range: {z_range:f}",
+                     f"    - Percent = {percent:f}",
+                     f"    - Terminate if absolute change < {self.term_thres:f}"):
+            self.print_msg(line)
 
     # subclass hooks ----------------------------------------------------------------
     def _method_params(self):
@@ -160,7 +164,6 @@ class FDPDEInpainter(ABC):
 
     def _inpaint_fused_init(self, image, mask, out):
         import ctypes
-        import threading
         lib = C.lib()
         code = C.HMI_F64 if image.dtype == np.float64 else C.HMI_F32
         if self.init_with.lower() == "zeros":
@@ -182,13 +185,8 @@ class FDPDEInpainter(ABC):
             self.set_term_criteria(image)
         self.print_msg("* Optimization:")
         params = self._make_params(image.shape[0], image.shape[1], image.dtype)
-        filler = threading.Thread(target=lib.hmi_host_fill_unknown,
-                                  args=(image.ctypes.data, mask.ctypes.data, image.size, code, value))
-        filler.start()
-        try:
-            out, st = inpaint_host(params, image, mask, out, fill=value)
-        finally:
-            filler.join()
+        # the library initialises the caller's array in place once the upload has read it
+        out, st = self._solve_host(params, image, mask, out, fill=value, init_host=True)
         self._record(st.updates_done, st.last_diff, bool(st.converged), None, None)
         self.history_.append((image.shape[0], image.shape[1], self.iterations_))
         if not self.converged_:
@@ -196,7 +194,25 @@ class FDPDEInpainter(ABC):
         return out
 
     def _device(self):
-        return 0 if self.device is None else int(self.device)
+        if self.device is None:
+            devs = self._device_list()
+            return devs[0] if devs else 0
+        return int(self.device)
+
+    def _device_list(self):
+        """The `devices` keyword resolved to a list of CUDA ordinals, or None for a single-GPU solve."""
+        if self.devices is None:
+            return None
+        if isinstance(self.devices, str):
+            if self.devices != "all":
+                raise ValueError("devices must be a list of CUDA ordinals or 'all'")
+            n = C.check(C.lib().hmi_device_count())
+            devs = list(range(n))
+        else:
+            devs = [int(d) for d in self.devices]
+        if not devs:
+            raise ValueError("devices must name at least one GPU")
+        return devs if len(devs) > 1 else None
 
     def _make_params(self, rows, cols, dtype, **over):
         kw = dict(rows=rows, cols=cols, dtype=dtype, method=self.METHOD,
@@ -218,10 +234,11 @@ class FDPDEInpainter(ABC):
             raise ZeroDivisionError("integer modulo by zero")  # what `i % 0` raises in the reference (:322)
         params = self._make_params(image.shape[0], image.shape[1], image.dtype)
         if not self.print_progress:
-            out, st = inpaint_host(params, image, mask, out)
+            out, st = self._solve_host(params, image, mask, out)
             self._record(st.updates_done, st.last_diff, bool(st.converged), None, None)
         else:
-            with Solver(params) as s:
+            devs = self._device_list()
+            with (Group(params, devs) if devs else Solver(params)) as s:
                 s.set_problem_host(image, mask)
                 done, diff, conv = self._loop(s, params.criteria)
                 out = s.get_result_host(out)
@@ -230,6 +247,13 @@ class FDPDEInpainter(ABC):
         if not self.converged_:
             print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
         return out
+
+    def _solve_host(self, params, image, mask, out, fill=None, init_host=False):
+        """One-shot solve over host buffers on one GPU or, with `devices`, on several of this process."""
+        devs = self._device_list()
+        if devs:
+            return inpaint_host_devices(params, devs, image, mask, out, fill=fill, init_host=init_host)
+        return inpaint_host(params, image, mask, out, fill=fill, init_host=init_host)
 
     def _record(self, done, diff, conv, kernel_name, launches):
         self.iterations_, self.last_diff_, self.converged_ = int(done), float(diff), bool(conv)
@@ -272,25 +296,21 @@ class FDPDEInpainter(ABC):
                 return i, diff, True
         return i, diff, False
 
-    # ------------------------------------------------------------------ printing utilities (:386-404)
-    def print_start(self, msg):
-        if self.print_progress:
-            print(msg, end='')
-            self.ts = timer()
-
-    def print_end(self):
-        if self.print_progress:
-            te = timer()
-            print("done ({:.2f} s)".format(te - self.ts))
-
+    # ------------------------------------------------------------------ verbose output (reference :386-404)
     def print_msg(self, msg):
         if self.print_progress:
             print(msg)
 
-    def get_decimal_places(self, number):
-        if math.floor(number) == number:
-            return 0
-        return len("{:f}".format(number).split(".")[1])
+    def print_start(self, msg):
+        """`msg` without a newline and start the stopwatch; print_end() closes the line with the time."""
+        if not self.print_progress:
+            return
+        print(msg, end="")
+        self.ts = timer()
+
+    def print_end(self):
+        if self.print_progress:
+            print("done ({:.2f} s)".format(timer() - self.ts))
 
 
 class _RangeView:

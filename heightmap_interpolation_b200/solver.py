@@ -141,6 +141,25 @@ class Solver:
         C.check(self._lib.hmi_sweeps_norm(self._h, int(n), stream, ctypes.byref(nm)))
         return Norm(nm.sum_d2, nm.sum_f2, nm.max_abs, nm.has_nan)
 
+    # -- peer-memory halo links (row slabs)
+    def halo_setup(self):
+        """Allocate this slab's halo block; returns HmiHaloInfo (device pointer + 64-byte CUDA IPC handle)."""
+        info = C.HmiHaloInfo()
+        C.check(self._lib.hmi_halo_setup(self._h, ctypes.byref(info)))
+        return info
+
+    def halo_connect(self, side, peer_block, peer_device):
+        C.check(self._lib.hmi_halo_connect(self._h, int(side), peer_block, int(peer_device)))
+
+    def halo_connect_ipc(self, side, handle):
+        handle = bytes(handle)
+        if len(handle) != 64:
+            raise ValueError("a CUDA IPC memory handle is 64 bytes")
+        C.check(self._lib.hmi_halo_connect_ipc(self._h, int(side), handle))
+
+    def sweeps_exchange(self, n, main_stream=0, side_stream=0):
+        C.check(self._lib.hmi_sweeps_exchange(self._h, int(n), main_stream, side_stream))
+
     def run(self, stream=0):
         st = C.HmiStatus()
         C.check(self._lib.hmi_run(self._h, stream, ctypes.byref(st)))
@@ -186,11 +205,130 @@ class Solver:
         return self._lib.hmi_kernel_name(self._h).decode()
 
 
-def inpaint_host(params, image, mask, out=None, fill=None):
+class Group:
+    """One grid cut into row slabs over several GPUs of this process (hmi_group_*): the engine behind
+    ``Inpainter(..., devices=[...])``.  Same sweeps()/sweeps_norm()/run() surface as Solver."""
+
+    def __init__(self, params, devices, exchange_every=0):
+        self._lib = C.lib()
+        self.params = params
+        devs = (ctypes.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        C.check(self._lib.hmi_group_create(ctypes.byref(params), devs, len(devices), int(exchange_every), ctypes.byref(h)))
+        self._h = h
+        self.np_dtype = np.float64 if params.dtype == C.HMI_F64 else np.float32
+        n, e, g = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        C.check(self._lib.hmi_group_info(self._h, ctypes.byref(n), ctypes.byref(e), ctypes.byref(g)))
+        self.n_slabs, self.exchange_every, self.ghost_rows = n.value, e.value, g.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hmi_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_problem_host(self, image, mask):
+        image = np.ascontiguousarray(image, dtype=self.np_dtype)
+        m8 = np.ascontiguousarray(mask).view(np.uint8) if mask.dtype == np.bool_ else \
+            np.ascontiguousarray(mask, dtype=np.uint8)
+        want = (self.params.rows, self.params.cols)
+        if image.shape != want or m8.shape != want:
+            raise ValueError("image/mask shape %s/%s, group expects %s" % (image.shape, m8.shape, want))
+        C.check(self._lib.hmi_group_set_problem_host(self._h, image.ctypes.data, image.strides[0],
+                                                     m8.ctypes.data, m8.strides[0]))
+
+    def fill_unknown(self, value):
+        C.check(self._lib.hmi_group_fill_unknown(self._h, float(value)))
+
+    def sweeps(self, n):
+        C.check(self._lib.hmi_group_sweeps(self._h, int(n)))
+
+    def sweeps_norm(self, n):
+        nm = C.HmiNorm()
+        C.check(self._lib.hmi_group_sweeps_norm(self._h, int(n), ctypes.byref(nm)))
+        return Norm(nm.sum_d2, nm.sum_f2, nm.max_abs, nm.has_nan)
+
+    def run(self):
+        st = C.HmiStatus()
+        C.check(self._lib.hmi_group_run(self._h, ctypes.byref(st)))
+        return st
+
+    def sync(self):
+        C.check(self._lib.hmi_group_sync(self._h))
+
+    def set_term_thres(self, term_thres):
+        C.check(self._lib.hmi_group_set_term_thres(self._h, float(term_thres)))
+        self.params.term_thres = float(term_thres)
+
+    def get_result_host(self, out=None):
+        p = self.params
+        if out is None:
+            out = np.empty((p.rows, p.cols), dtype=self.np_dtype)
+            if out.nbytes >= (1 << 22):
+                self._lib.hmi_host_prefault(out.ctypes.data, out.nbytes)
+        C.check(self._lib.hmi_group_get_result_host(self._h, out.ctypes.data, out.strides[0]))
+        return out
+
+    def slab(self, i):
+        """(raw solver handle, first row, end row) of slab i — for tests."""
+        h, a, b = ctypes.c_void_p(), ctypes.c_int32(), ctypes.c_int32()
+        C.check(self._lib.hmi_group_slab(self._h, int(i), ctypes.byref(h), ctypes.byref(a), ctypes.byref(b)))
+        return h, a.value, b.value
+
+    @property
+    def launch_count(self):
+        return self._lib.hmi_group_launch_count(self._h)
+
+    @property
+    def kernel_name(self):
+        h, _, _ = self.slab(0)
+        return self._lib.hmi_kernel_name(h).decode()
+
+    @property
+    def temporal_block(self):
+        h, _, _ = self.slab(0)
+        return self._lib.hmi_temporal_block(h)
+
+
+def inpaint_host_devices(params, devices, image, mask, out=None, fill=None, init_host=False):
+    """hmi_inpaint_host_devices: the one-shot call over several GPUs of this process."""
+    lib = C.lib()
+    np_dtype = np.float64 if params.dtype == C.HMI_F64 else np.float32
+    image = np.ascontiguousarray(image, dtype=np_dtype)
+    m8 = np.ascontiguousarray(mask).view(np.uint8) if mask.dtype == np.bool_ else \
+        np.ascontiguousarray(mask, dtype=np.uint8)
+    if out is None:
+        out = np.empty_like(image)
+        if out.nbytes >= (1 << 22):
+            lib.hmi_host_prefault(out.ctypes.data, out.nbytes)
+    elif out.shape != image.shape or out.dtype != image.dtype or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous array of the image's shape and dtype")
+    devs = (ctypes.c_int32 * len(devices))(*[int(d) for d in devices])
+    st = C.HmiStatus()
+    C.check(lib.hmi_inpaint_host_devices(ctypes.byref(params), devs, len(devices), image.ctypes.data, m8.ctypes.data,
+                                         0 if fill is None else (2 if init_host else 1),
+                                         0.0 if fill is None else float(fill),
+                                         out.ctypes.data, ctypes.byref(st)))
+    return out, st
+
+
+def inpaint_host(params, image, mask, out=None, fill=None, init_host=False):
     """hmi_inpaint_host: one call, host buffers in, host buffer out.  `out` (optional) is a
     C-contiguous array of the grid's shape and dtype to receive the result, e.g. pinned memory.
     `fill` (optional) = value the unknown cells take on the device after the upload
-    (hmi_inpaint_host_fill: the 'zeros' / 'mean' initialiser fused in)."""
+    (hmi_inpaint_host_fill: the 'zeros' / 'mean' initialiser fused in); with `init_host` the unknown
+    cells of `image` itself take it too, once the upload has read the array (hmi_inpaint_host_init)."""
     lib = C.lib()
     np_dtype = np.float64 if params.dtype == C.HMI_F64 else np.float32
     image = np.ascontiguousarray(image, dtype=np_dtype)
@@ -207,6 +345,7 @@ def inpaint_host(params, image, mask, out=None, fill=None):
         C.check(lib.hmi_inpaint_host(ctypes.byref(params), image.ctypes.data, m8.ctypes.data,
                                      out.ctypes.data, ctypes.byref(st)))
     else:
-        C.check(lib.hmi_inpaint_host_fill(ctypes.byref(params), image.ctypes.data, m8.ctypes.data,
-                                          float(fill), out.ctypes.data, ctypes.byref(st)))
+        fn = lib.hmi_inpaint_host_init if init_host else lib.hmi_inpaint_host_fill
+        C.check(fn(ctypes.byref(params), image.ctypes.data, m8.ctypes.data, float(fill), out.ctypes.data,
+                   ctypes.byref(st)))
     return out, st

@@ -136,6 +136,37 @@ int hmi_sweeps(hmi_solver *s, int64_t n, void *stream);
  * next call, so the exchange overlaps the interior update.  Halos must be fresh on entry. */
 int hmi_sweeps_overlap(hmi_solver *s, int64_t n, void *main_stream, void *side_stream);
 
+/* Peer-memory halo links between row slabs — the multi-GPU data path (csrc/hmi_halo.cu).  The
+ * reference has nothing comparable (one process, whole grid in RAM: fd_pde_inpainter.py:281-366);
+ * these calls replace what a grouped ncclSend/ncclRecv per neighbour would do, without occupying SMs:
+ * the producer's copy engine pushes its rows next to a seam into a staging area in the neighbour's HBM
+ * (double buffered by exchange parity) and publishes the exchange number in a flag there with a stream
+ * memory operation; the consumer's next temporal block waits for the flag and moves the rows into its
+ * ghost rows.  Works between devices of one process (hmi_halo_connect) and between processes
+ * (hmi_halo_connect_ipc with the 64-byte CUDA IPC handle hmi_halo_setup returns; exchange the handles
+ * with any transport, e.g. torch.distributed.all_gather).  All slabs of one solve must use the same
+ * ghost depth and call the same sequence of hmi_sweeps* functions.  Nobody may destroy a slab while a
+ * neighbour can still push into it (synchronise / barrier first). */
+typedef struct hmi_halo_info {
+    void *block;                  /* this slab's halo block (device pointer, valid in this process) */
+    uint64_t block_bytes;
+    int32_t device;
+    int32_t reserved;
+    unsigned char ipc_handle[64]; /* cudaIpcMemHandle_t of `block` */
+} hmi_halo_info;
+int hmi_halo_setup(hmi_solver *s, hmi_halo_info *out);
+/* side 0 = the slab above (it feeds my top ghost rows), side 1 = the slab below */
+int hmi_halo_connect(hmi_solver *s, int32_t side, void *peer_block, int32_t peer_device);
+int hmi_halo_connect_ipc(hmi_solver *s, int32_t side, const unsigned char *ipc_handle);
+
+/* n <= exchange depth sweeps on a linked slab, then the halo exchange of the result, overlapped with
+ * the interior update of the last temporal block: stale or in-flight ghost rows are brought up to date
+ * first; the rows next to the seams are produced first on `side_stream` (NULL = the solver's own
+ * high-priority stream) and pushed to the neighbours from there while `main_stream` still updates the
+ * interior.  hmi_sweeps / hmi_sweeps_norm on a linked slab refresh the ghost rows themselves too, but
+ * leave them stale (no push). */
+int hmi_sweeps_exchange(hmi_solver *s, int64_t n, void *main_stream, void *side_stream);
+
 /* n sweeps (n >= 1); the convergence sums between the last two iterates are reduced on the device,
  * fused into the last sweep, and returned (synchronises `stream`).
  * Replaces: the loop body + term_check() on a check iteration (fd_pde_inpainter.py:322-323, 368-379). */
@@ -163,6 +194,12 @@ int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t 
 int hmi_inpaint_host_fill(const hmi_params *params, const void *image, const uint8_t *mask, double fill_value,
                           void *out, hmi_status *status);
 
+/* hmi_inpaint_host_fill that also initialises the caller's array in place (unknown cells of `image` <-
+ * fill_value, what Initializer.initialize does first: inpainting/initializer.py:15-18) — on a host
+ * thread, after the upload has read the array and while the device solves. */
+int hmi_inpaint_host_init(const hmi_params *params, void *image, const uint8_t *mask, double fill_value, void *out,
+                          hmi_status *status);
+
 /* Multigrid (FDPDEInpainter.inpaint_multigrid, inpainting/fd_pde_inpainter.py:255-264): load the next
  * finer level into `fine` — upload its image and mask like hmi_set_problem_host, then replace the
  * device copy by
@@ -184,6 +221,34 @@ int hmi_set_problem_host_blend(hmi_solver *fine, const void *image, size_t image
                                size_t mask_pitch_bytes, hmi_solver *coarse, const int32_t *sx, const int32_t *sx1,
                                const void *ax0, const void *ax1, const int32_t *sy, const int32_t *sy1,
                                const void *by0, const void *by1, int32_t scrub_nan, hmi_blend_info *info);
+
+/* Several GPUs driven by one process: the grid is cut into contiguous row slabs, one per device,
+ * linked through peer memory (hmi_halo_*), and all of them are driven by the calling thread.  This is
+ * what `Inpainter(..., devices=[...]).inpaint(image, mask)` runs on, so that the reference's single call
+ * site (apps/interpolate_netcdf4.py:200-204) can use the whole box.  `params` describes the whole grid
+ * (ghost_* = 0; `device` is ignored); `exchange_every` = sweeps between halo exchanges (0 = default: 18
+ * for the radius-1 methods, 12 for CCST), each slab carries radius * exchange_every ghost rows.  Small
+ * grids use fewer devices than listed.  The functions mirror their single-solver namesakes. */
+typedef struct hmi_group hmi_group;
+int hmi_group_create(const hmi_params *params, const int32_t *devices, int32_t n_devices, int32_t exchange_every,
+                     hmi_group **out);
+void hmi_group_destroy(hmi_group *g);
+int hmi_group_set_problem_host(hmi_group *g, const void *image, size_t image_pitch_bytes, const uint8_t *mask,
+                               size_t mask_pitch_bytes);
+int hmi_group_fill_unknown(hmi_group *g, double value);      /* 'zeros' / 'mean' initialiser on the device copies */
+int hmi_group_sweeps(hmi_group *g, int64_t n);
+int hmi_group_sweeps_norm(hmi_group *g, int64_t n, hmi_norm *out);
+int hmi_group_run(hmi_group *g, hmi_status *status);         /* FDPDEInpainter.inpaint_grid, fd_pde_inpainter.py:281-366 */
+int hmi_group_set_term_thres(hmi_group *g, double term_thres);
+int hmi_group_get_result_host(hmi_group *g, void *out, size_t out_pitch_bytes);
+int hmi_group_sync(hmi_group *g);
+int hmi_group_info(const hmi_group *g, int32_t *n_slabs, int32_t *exchange_every, int32_t *ghost_rows);
+int hmi_group_slab(hmi_group *g, int32_t i, hmi_solver **solver, int32_t *row0, int32_t *row1);
+int64_t hmi_group_launch_count(const hmi_group *g);
+/* One-shot over host buffers on several devices.  fill: 0 = hmi_inpaint_host, 1 = hmi_inpaint_host_fill,
+ * 2 = hmi_inpaint_host_init (`image` is then written: its unknown cells take fill_value). */
+int hmi_inpaint_host_devices(const hmi_params *params, const int32_t *devices, int32_t n_devices, const void *image,
+                             const uint8_t *mask, int32_t fill, double fill_value, void *out, hmi_status *status);
 
 /* Multi-GPU plumbing: device address and row pitch (bytes) of the current iterate and of the mask,
  * so the host layer can exchange ghost rows with NCCL (row 0 = first ghost row).  The addresses
@@ -223,7 +288,9 @@ int hmi_host_prefault(void *buf, size_t bytes);
 int hmi_release_cache(void);
 
 /* Tuning knobs for tests and benchmarks: "chunk_rows" (rows per warp chunk of the streaming kernel,
- * 0 = wave-aware automatic choice, -1 = the older fixed rule) and "temporal_block" (sweeps fused per launch). */
+ * 0 = wave-aware automatic choice, -1 = the older fixed rule), "temporal_block" (sweeps fused per launch),
+ * "vec" (fp64 cells per lane: 2 or 4) and "tma" (row staging of the harmonic / CCST kernel: 0 = cp.async
+ * ring, 1 = one 1-D bulk copy per row, 2 = 2-D tensor-map boxes on interior strips). */
 int hmi_set_option(hmi_solver *s, const char *key, int64_t value);
 
 /* Replace the stop threshold of hmi_run.  'absolute_percent' scales term_thres by the z-range of the
