@@ -101,6 +101,10 @@ SYMBOLS = {
                                              ctypes.POINTER(HmiStatus)]),
     "hmi_set_problem_host_blend": (ctypes.c_int, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                   ctypes.c_int32, ctypes.POINTER(HmiBlendInfo)]),
+    "hmi_step_fun_host": (ctypes.c_int, [ctypes.POINTER(HmiParams), _vp, _sz, _vp, _sz, _vp, _sz]),
+    "hmi_convolve3x3_host": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _sz,
+                                            ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.c_int32, _vp, _sz,
+                                            _vp, _sz]),
     "hmi_current_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_mask_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_host_fill_unknown": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, ctypes.c_double]),

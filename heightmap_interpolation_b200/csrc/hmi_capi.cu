@@ -191,6 +191,38 @@ __global__ void fill_unknown_kernel(T *f, long long pitch, const uint8_t *m, lon
 
 namespace hmi {
 
+// Tensor maps for the 2-D TMA staging of the streaming kernel (tma == 2): one per ping-pong grid and
+// one for the mask, boxes of 32*V columns x STREAM_BOX_ROWS rows, encoded once per solver and V.
+static int ensure_tmaps(hmi_solver *s, int V)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    if (s->tmaps && s->tmaps_v == V) return HMI_OK;
+    const DriverApi *drv = driver_api();
+    if (!drv) return HMI_ERR_CUDA;
+    if (!s->tmaps) s->tmaps = new (std::nothrow) CUtensorMap[3];
+    if (!s->tmaps) return fail(HMI_ERR_CUDA, "out of host memory");
+    const cuuint32_t box[2] = {(cuuint32_t)(32 * V), (cuuint32_t)STREAM_BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 3; ++i) {
+        const bool is_mask = (i == 2);
+        const cuuint64_t dims[2] = {(cuuint64_t)(is_mask ? s->mpitch : s->pitch), (cuuint64_t)s->phys_rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)(is_mask ? s->mpitch : s->pitch * s->elem)};
+        const CUtensorMapDataType dt = is_mask ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                               : (s->elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        void *base = is_mask ? (void *)s->mask : (void *)s->buf[i];
+        const CUresult r = drv->tensorMapEncodeTiled(&s->tmaps[i], dt, 2, base, dims, strides, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            delete[] s->tmaps;
+            s->tmaps = nullptr;
+            return fail(HMI_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        }
+    }
+    s->tmaps_v = V;
+    return HMI_OK;
+}
+
 template <typename T>
 static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaStream_t st, bool flip)
 {
@@ -234,6 +266,13 @@ static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaS
         a.chunk_rows = s->chunk_rows;
         a.vec = s->vec;
         a.tma = s->tma;
+        if (s->tma == 2) {
+            const int rc = ensure_tmaps(s, hmi::stream_cells_per_lane(p.dtype, s->vec));
+            if (rc != HMI_OK) return rc;
+            a.tmap_f = s->tmaps[s->cur];
+            a.tmap_m = s->tmaps[2];
+            a.phys_row0 = p.ghost_top;
+        }
         a.dt = (T)dt_eff; a.tension = (T)p.tension; a.one_minus_tension = (T)(1.0 - p.tension);
         a.do_norm = do_norm ? 1 : 0;
         a.partials = s->d_partials; a.counter = s->d_counter; a.result = s->d_result;

@@ -133,4 +133,14 @@ template <typename T>
 cudaError_t launch_generic(int method, const SweepArgs<T> &a, cudaStream_t st, int *nblocks_out);
 int generic_max_blocks(int rows_total, int cols);
 
+// one evaluation of the step function on a whole grid (a.mask = work mask or null; a.dst = step)
+template <typename T>
+cudaError_t launch_generic_step(int method, const SweepArgs<T> &a, cudaStream_t st);
+
+// one 3x3 filter (Convolver.__call__)
+struct Kernel9 { double w[9]; };
+template <typename T>
+cudaError_t launch_conv3x3(const T *src, T *dst, long long pitch, const uint8_t *mask, long long mpitch, int rows, int cols,
+                           int border, int s, const Kernel9 &k, cudaStream_t st);
+
 }  // namespace hmi

@@ -173,6 +173,81 @@ __global__ void __launch_bounds__(GEN_BX *GEN_BY) generic_sweep_kernel(const Swe
     if (a.do_norm) block_norm_reduce(d2, f2, mx, nanf, sh, a.partials, a.counter, a.result);
 }
 
+// step_fun(f, mask) of the reference (abstract hook fd_pde_inpainter.py:406-408, the four subclasses):
+// out = step where the work mask is set (or everywhere without one), the input value elsewhere —
+// what a masked convolver leaves in cells it does not evaluate (convolve_at_mask.py:46).
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(GEN_BX *GEN_BY) generic_step_kernel(const SweepArgs<T> a)
+{
+    const int j = blockIdx.x * GEN_BX + threadIdx.x;
+    const int i = blockIdx.y * GEN_BY + threadIdx.y;
+    if (j >= a.cols || i >= a.rows) return;
+    Field<T> g{a.src, a.pitch, a.rows, a.cols, a.border, 1, 1};
+    const long long o = (long long)i * a.pitch + j;
+    const bool work = !a.mask || a.mask[(long long)i * a.mpitch + j];
+    a.dst[o] = work ? step_at<T, METHOD>(g, a, i, j) : a.src[o];
+}
+
+template <typename T>
+cudaError_t launch_generic_step(int method, const SweepArgs<T> &a, cudaStream_t st)
+{
+    dim3 grid((a.cols + GEN_BX - 1) / GEN_BX, (a.rows + GEN_BY - 1) / GEN_BY), block(GEN_BX, GEN_BY);
+    switch (method) {
+    case HMI_HARMONIC: generic_step_kernel<T, HMI_HARMONIC><<<grid, block, 0, st>>>(a); break;
+    case HMI_CCST:     generic_step_kernel<T, HMI_CCST><<<grid, block, 0, st>>>(a); break;
+    case HMI_TV:       generic_step_kernel<T, HMI_TV><<<grid, block, 0, st>>>(a); break;
+    default:           generic_step_kernel<T, HMI_AMLE><<<grid, block, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_generic_step<float>(int, const SweepArgs<float> &, cudaStream_t);
+template cudaError_t launch_generic_step<double>(int, const SweepArgs<double> &, cudaStream_t);
+
+// Convolver.__call__(image, kernel, mask) of the reference (convolver.py:28-29): one 3x3 filter with
+// the convolver's orientation (s = +1 correlation, -1 true convolution: the kernel flipped in both
+// axes) and border rule, evaluated where `mask` is set (everywhere without one) and copying the input
+// elsewhere (convolve_at_mask.py:46).  Taps in row-major order of the (flipped) kernel, every tap
+// multiplied and added — zero weights included, like the numba loops (convolve_at_mask.py:51-62) —
+// double accumulator, one rounding to the grid dtype at the end.
+template <typename T>
+__global__ void __launch_bounds__(GEN_BX *GEN_BY) conv3x3_kernel(const T *__restrict__ src, T *__restrict__ dst,
+                                                                 long long pitch, const uint8_t *__restrict__ mask,
+                                                                 long long mpitch, int rows, int cols, int border, int s,
+                                                                 Kernel9 k)
+{
+    const int j = blockIdx.x * GEN_BX + threadIdx.x;
+    const int i = blockIdx.y * GEN_BY + threadIdx.y;
+    if (j >= cols || i >= rows) return;
+    const long long o = (long long)i * pitch + j;
+    if (mask && !mask[(long long)i * mpitch + j]) { dst[o] = src[o]; return; }
+    Field<T> g{src, pitch, rows, cols, border, 1, 1};
+    double num = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            // correlation: weight k[a][b] on f[i-1+a][j-1+b]; convolution: weight k[2-a][2-b] on the same cell
+            const double w = s > 0 ? k.w[3 * a + b] : k.w[3 * (2 - a) + (2 - b)];
+            num += w * (double)g.F(i - 1 + a, j - 1 + b);
+        }
+    dst[o] = (T)num;
+}
+
+template <typename T>
+cudaError_t launch_conv3x3(const T *src, T *dst, long long pitch, const uint8_t *mask, long long mpitch, int rows, int cols,
+                           int border, int s, const Kernel9 &k, cudaStream_t st)
+{
+    dim3 grid((cols + GEN_BX - 1) / GEN_BX, (rows + GEN_BY - 1) / GEN_BY), block(GEN_BX, GEN_BY);
+    conv3x3_kernel<T><<<grid, block, 0, st>>>(src, dst, pitch, mask, mpitch, rows, cols, border, s, k);
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_conv3x3<float>(const float *, float *, long long, const uint8_t *, long long, int, int, int, int,
+                                           const Kernel9 &, cudaStream_t);
+template cudaError_t launch_conv3x3<double>(const double *, double *, long long, const uint8_t *, long long, int, int, int,
+                                            int, const Kernel9 &, cudaStream_t);
+
 int generic_max_blocks(int rows_total, int cols)
 {
     return ((cols + GEN_BX - 1) / GEN_BX) * ((rows_total + GEN_BY - 1) / GEN_BY);

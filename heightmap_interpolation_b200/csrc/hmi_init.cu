@@ -184,7 +184,86 @@ __global__ void upsample_blend_kernel(T *__restrict__ f, long long pitch, const 
     }
 }
 
+// The same level transition for a pyramid that lives on the device(s): the level's image and mask are
+// gathered with stride 2^l from the finest level (halve_image applied l times picks every 2^l-th cell,
+// misc/image_proc.py:4-12; the mask is ANDed with "not NaN", fd_pde_inpainter.py:223-224), the coarser
+// solution is up-sampled from wherever its row slabs live (peer memory included) and blended in.
+template <typename T>
+__device__ __forceinline__ const T *view_row(const SlabView &v, int y)
+{
+    int k = 0;
+    while (k + 1 < v.n && y >= v.row0[k + 1]) ++k;
+    return reinterpret_cast<const T *>(v.base[k] + (long long)(y - v.row0[k]) * v.pitch);
+}
+
+template <typename T>
+__global__ void pyramid_blend_kernel(const PyramidBlend<T> a)
+{
+    typedef Op<T> O;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double lo = INFINITY, hi = -INFINITY, nanv = 0.0;
+    if (j < a.cols) {
+        const int x0 = a.sx[j], x1 = a.sx1[j];
+        const T a0 = a.ax0[j], a1 = a.ax1[j];
+        for (int p = blockIdx.y; p < a.phys_rows; p += gridDim.y) {
+            const int i = a.row_first + p;                       // row of this level's (global) grid
+            const T *c0 = view_row<T>(a.coarse, a.sy[i]), *c1 = view_row<T>(a.coarse, a.sy1[i]);
+            const T t0 = O::add(O::mul(c0[x0], a0), O::mul(c0[x1], a1));
+            const T t1 = O::add(O::mul(c1[x0], a0), O::mul(c1[x1], a1));
+            const T up = O::add(O::mul(t0, a.by0[i]), O::mul(t1, a.by1[i]));
+            T img;
+            bool known;
+            if (a.stride == 1) {                                 // the finest level itself, in place
+                img = a.f[(long long)p * a.pitch + j];
+                known = a.mask[(long long)p * a.mpitch + j] != 0;
+                if (a.scrub_nan && img != img) { img = T(0); *a.nan_flag = 1; }
+            } else {
+                img = view_row<T>(a.fine_img, i * a.stride)[(long long)j * a.stride];
+                known = view_row<uint8_t>(a.fine_mask, i * a.stride)[(long long)j * a.stride] != 0 && img == img;
+                a.mask[(long long)p * a.mpitch + j] = known ? 1 : 0;
+            }
+            const T m = known ? T(1) : T(0);
+            const T v = O::add(O::mul(up, T(1) - m), O::mul(img, m));
+            a.f[(long long)p * a.pitch + j] = v;
+            const double d = (double)v;
+            if (d != d) nanv = 1.0;
+            lo = d < lo ? d : lo;
+            hi = d > hi ? d : hi;
+        }
+    }
+    __shared__ double sh[3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nanv = fmax(nanv, __shfl_xor_sync(0xffffffffu, nanv, o));
+    }
+    if (lane == 0) { sh[0][warp] = lo; sh[1][warp] = hi; sh[2][warp] = nanv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 1; w < nw; ++w) {
+            lo = fmin(lo, sh[0][w]); hi = fmax(hi, sh[1][w]); nanv = fmax(nanv, sh[2][w]);
+        }
+        const long long b = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        a.partials[3 * b + 0] = lo; a.partials[3 * b + 1] = hi; a.partials[3 * b + 2] = nanv;
+    }
+}
+
 }  // namespace
+
+template <typename T>
+cudaError_t launch_pyramid_blend(const PyramidBlend<T> &a, int *nblocks, cudaStream_t st)
+{
+    const dim3 grid((a.cols + 127) / 128, a.phys_rows < UPSAMPLE_MAX_GRID_Y ? a.phys_rows : UPSAMPLE_MAX_GRID_Y);
+    *nblocks = (int)(grid.x * grid.y);
+    pyramid_blend_kernel<T><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_pyramid_blend<float>(const PyramidBlend<float> &, int *, cudaStream_t);
+template cudaError_t launch_pyramid_blend<double>(const PyramidBlend<double> &, int *, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_upsample_blend(T *f, long long pitch, const uint8_t *mask, long long mpitch, int rows, int cols,

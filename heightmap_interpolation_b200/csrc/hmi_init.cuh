@@ -26,4 +26,33 @@ cudaError_t launch_upsample_blend(T *f, long long pitch, const uint8_t *mask, lo
                                   const T *ax1, const int *sy, const int *sy1, const T *by0, const T *by1,
                                   int scrub_nan, double *partials, int *nan_flag, int *nblocks, cudaStream_t st);
 
+// A grid cut into row slabs that may live on several devices (all readable from the launching one):
+// slab k holds global rows [row0[k], row0[k+1]); base[k] points at its row row0[k].
+constexpr int MAX_VIEW_SLABS = 16;
+struct SlabView {
+    int n;
+    int row0[MAX_VIEW_SLABS + 1];
+    const char *base[MAX_VIEW_SLABS];
+    long long pitch;                 // bytes per row
+};
+
+// One slab of one pyramid level: image and mask gathered with `stride` from the finest level (stride 1 =
+// the finest level itself, blended in place), unknown cells <- bilinear up-sampling of the coarser solution.
+template <typename T>
+struct PyramidBlend {
+    T *f;                            // this slab, physical row 0 (ghost rows included)
+    uint8_t *mask;
+    long long pitch, mpitch;         // elements / bytes per row
+    int phys_rows, cols;
+    int row_first;                   // row of the level's grid that physical row 0 is
+    int stride, scrub_nan;
+    SlabView fine_img, fine_mask, coarse;
+    const int *sx, *sx1, *sy, *sy1;  // taps: per column, per row of the level's grid
+    const T *ax0, *ax1, *by0, *by1;
+    double *partials;                // (min, max, nan) per block
+    int *nan_flag;
+};
+template <typename T>
+cudaError_t launch_pyramid_blend(const PyramidBlend<T> &a, int *nblocks, cudaStream_t st);
+
 }  // namespace hmi

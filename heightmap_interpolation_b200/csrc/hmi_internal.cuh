@@ -87,6 +87,7 @@ struct hmi_solver {
     int halo_state = 0;             // 0 = ghost rows fresh, 1 = pushes in flight (wait + copy in), 2 = stale
     bool linked = false;
     CUtensorMap *tmaps = nullptr;   // host copies of the tensor maps of buf[0], buf[1], mask (tma == 2)
+    int tmaps_v = 0;                // cells per lane they were encoded for
 };
 
 namespace hmi {

@@ -70,6 +70,13 @@ struct Geo {
     // bulk copies; D mbarriers per warp follow the ring
     static constexpr int MB_T = ((32 * V + 16 + 15) / 16) * 16;
     static constexpr int SLOT_T = ROW_BYTES + MB_T;
+    // 2-D tensor-map staging (interior strips): boxes of RB rows x 32*V columns of f and of the mask,
+    // NBX boxes in flight per warp, one mbarrier per box.  RB = 3 matches the x3 unrolled row loop, so
+    // the wait sits in phase 0 and the refill in phase 2 with no run-time row counter.
+    static constexpr int RB = 3, NBX = 4;
+    static constexpr int FBOX = RB * ROW_BYTES;
+    static constexpr int MBOX = ((RB * 32 * V + 127) / 128) * 128;
+    static constexpr int RING_T2 = ((NBX * (FBOX + MBOX) + NBX * 8 + 127) / 128) * 128;
     static_assert(V % N == 0 && NCH >= 1, "a lane moves whole 16-byte chunks");
     static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
     static_assert(S > 0, "temporal block too deep for this strip width");
@@ -97,18 +104,22 @@ __device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], cons
 // One warp streams its strip down one chunk of rows.  MODE 2 = the strip touches a grid edge (ghost
 // columns to mirror, rows to reflect or clamp); interior strips skip all of that and address
 // memory incrementally.  NORM = accumulate the convergence sums of the (single) sweep.
-template <typename T, int V, int K, int METHOD, int D, int MODE, bool NORM, bool TMA>
+template <typename T, int V, int K, int METHOD, int D, int MODE, bool NORM, int STG>
 __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsigned ring_s, const int lane,
                                             const int win, const int y0, const int y1, double &n_d2, double &n_f2,
                                             double &n_mx, double &n_nan)
 {
     typedef Geo<T, V, K, METHOD> G;
     typedef typename Chunk16<T>::type C16;
+    // row staging: 0 = per-lane cp.async ring, 1 = one 1-D bulk copy per row, 2 = 2-D tensor-map boxes
+    constexpr bool TMA = (STG == 1), T2 = (STG == 2);
     constexpr int N = G::N, NCH = G::NCH, R = G::R, H = G::H, HV = G::HV, S = G::S;
     constexpr int ROW_BYTES = G::ROW_BYTES, SLOT = TMA ? G::SLOT_T : G::SLOT;
     constexpr bool CC = (METHOD == HMI_CCST);
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int SK = G::SK, LAG = G::LAG;
+    constexpr int RB = G::RB, NBX = G::NBX, FBOX = G::FBOX, MBOX = G::MBOX;
+    static_assert(!T2 || MODE == 0, "tensor-map boxes serve interior strips only");
     static_assert((LAG + 1) * V <= 64, "mask history does not fit 64 bits");
     static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
 
@@ -184,7 +195,33 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         __syncwarp();
     }
 
+    // T2: lane 0 fetches box `bi` (rows ybeg + RB*bi ...) of f and of the mask into slot `slot`
+    const unsigned t2_f = ring_s, t2_m = ring_s + NBX * FBOX, t2_bar = ring_s + NBX * (FBOX + MBOX);
+    auto issue_box = [&](const int bi, const unsigned slot) {
+        const int ybox = ybeg + RB * bi;
+        if (ybox < yend && lane == 0) {
+            const unsigned bar = t2_bar + 8 * slot;
+            fence_proxy_async();                   // the slot's previous contents were read with ld.shared
+            mbar_expect_tx(bar, (unsigned)(FBOX + RB * 32 * V));
+            tma_load_2d(t2_f + slot * FBOX, &a.tmap_f, x0, ybox + a.phys_row0, bar);
+            tma_load_2d(t2_m + slot * MBOX, &a.tmap_m, x0, ybox + a.phys_row0, bar);
+        }
+    };
+    if (T2) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NBX; ++i) mbar_init(t2_bar + 8 * i, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NBX; ++i) issue_box(i, (unsigned)i);
+    }
+    int t2_box = 0;                                            // box being consumed
+    unsigned t2_slot = 0, t2_par = 0;                          // ... its slot and mbarrier parity
+
     auto issue = [&]() {
+        if (T2) return;
         if (TMA) {
             if (ynext < yend && lane == 0) {
                 int ry = ynext;
@@ -231,8 +268,10 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
     };
 
+    if (!T2) {
 #pragma unroll
-    for (int u = 0; u < D - 1; ++u) issue();
+        for (int u = 0; u < D - 1; ++u) issue();
+    }
 
     unsigned rofs = 0;                                         // ring byte offset of the slot to read
     unsigned ridx = 0, rphase = 0;                             // TMA: slot index and mbarrier parity
@@ -241,7 +280,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     auto step = [&](auto ph, const int y) {
         constexpr int PH = decltype(ph)::value;
         constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
-        if (TMA) {
+        if (T2) {
+            if (PH == 0 && y < yend) mbar_wait(t2_bar + 8 * t2_slot, t2_par);   // the box rows y, y+1, y+2 sit in has landed
+        } else if (TMA) {
             if (y < yend) mbar_wait(bar_s + 8 * ridx, rphase);   // both bulk copies of row y have landed
         } else {                                   // (no row is fetched for the drain steps of the skew)
             cp_async_wait<D - 2>();                // this lane's copies of row y have landed
@@ -250,13 +291,26 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             T e[N];
-            lds16(TMA ? ring_s + rofs + lane * (16 * NCH) + c * 16 : ring_f + rofs + c * 512, e);
+            lds16(T2 ? t2_f + t2_slot * FBOX + PH * ROW_BYTES + lane * (16 * NCH) + c * 16
+                     : (TMA ? ring_s + rofs + lane * (16 * NCH) + c * 16 : ring_f + rofs + c * 512), e);
 #pragma unroll
             for (int q = 0; q < N; ++q) F[0][IN][c * N + q] = e[q];
         }
         // mask bytes are 0/1: one multiply packs them into V bits, cell v -> bit V-1-v
         unsigned mb;
-        {
+        if (T2) {
+            // the box starts at column x0, so this lane's V mask bytes sit at byte V*lane of the row
+            const unsigned ma = t2_m + t2_slot * MBOX + PH * (32 * V) + lane * V;
+            if (V == 4) mb = (lds32(ma) * 0x08040201u) >> 24;
+            else mb = ((lds16u(ma) * 0x0201u) >> 8) & 3u;
+            if (PH == 2) {                         // last row of the box: refill its slot with box t2_box + NBX
+                __syncwarp();                      // every lane is done with the slot
+                issue_box(t2_box + NBX, t2_slot);
+                t2_box += 1;
+                t2_slot = (t2_slot + 1 == NBX) ? 0u : t2_slot + 1;
+                if (t2_slot == 0) t2_par ^= 1u;
+            }
+        } else {
             unsigned w, sh = msh;
             if (TMA) {
                 const unsigned off = (unsigned)(x0 - mx16) + (unsigned)(V * lane);
@@ -391,19 +445,35 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         if (y + 1 < ystop) step(Phase<1>(), y + 1);
         if (y + 2 < ystop) step(Phase<2>(), y + 2);
     }
-    if (!TMA) cp_async_wait<0>();
+    if (!TMA && !T2) cp_async_wait<0>();
+    // T2: every box that was issued has been waited for (boxes start below yend and the loop runs to
+    // ystop >= yend), so no bulk copy is in flight when the warp leaves
 }
 
-template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM, bool TMA>
-__global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs<T> a)
+template <int A, int B> struct MaxOf { static constexpr int value = A > B ? A : B; };
+
+template <typename T, int V, int K, int METHOD, int D, int STG>
+struct WarpRing {
+    typedef Geo<T, V, K, METHOD> G;
+    static constexpr int CP = D * G::SLOT;                                             // cp.async ring (also the edge strips of STG 2)
+    static constexpr int value = STG == 1 ? ((D * G::SLOT_T + D * 8 + 15) / 16) * 16
+                                          : (STG == 2 ? MaxOf<((CP + 127) / 128) * 128, G::RING_T2>::value : CP);
+};
+
+template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM, int STG>
+__global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const __grid_constant__ StreamArgs<T> a)
 {
     typedef Geo<T, V, K, METHOD> G;
-    constexpr int WARP_RING = TMA ? ((D * G::SLOT_T + D * 8 + 15) / 16) * 16 : D * G::SLOT;
+    constexpr int WARP_RING = WarpRing<T, V, K, METHOD, D, STG>::value;
+    constexpr int STG_EDGE = STG == 2 ? 0 : STG;       // strips at a grid edge keep the per-lane copies
     extern __shared__ __align__(128) unsigned char ring_all[];
     __shared__ double sh[NORM ? 128 : 1];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const unsigned ring_s = smem_u32(ring_all) + (unsigned)wib * WARP_RING;
+    // tensor-map boxes must land on 128-byte boundaries, which a dynamic shared-memory base does not
+    // guarantee (the launcher reserves 128 spare bytes for STG 2)
+    const unsigned ring_0 = STG == 2 ? ((smem_u32(ring_all) + 127u) & ~127u) : smem_u32(ring_all);
+    const unsigned ring_s = ring_0 + (unsigned)wib * WARP_RING;
     const long long gw = (long long)blockIdx.x * WPB + wib;
     double n_d2 = 0.0, n_f2 = 0.0, n_mx = 0.0, n_nan = 0.0;
 
@@ -435,11 +505,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
         const bool row_edge = (ybeg < 0 && a.top_border) || (yend > a.rows && a.bottom_border) ||
                               (ybeg < a.read_lo) || (yend > a.read_hi);
         if (col_edge)
-            stream_rows<T, V, K, METHOD, D, 2, NORM, TMA>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 2, NORM, STG_EDGE>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else if (row_edge)
-            stream_rows<T, V, K, METHOD, D, 1, NORM, TMA>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 1, NORM, STG_EDGE>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows<T, V, K, METHOD, D, 0, NORM, TMA>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 0, NORM, STG>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -447,16 +517,16 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const StreamArgs
 // ------------------------------------------------------------------------------------------------
 // host side
 
-template <typename T, int V, int K, int METHOD, bool NORM, bool TMA>
+template <typename T, int V, int K, int METHOD, bool NORM, int STG>
 static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nblocks_out)
 {
     typedef Geo<T, V, K, METHOD> G;
     constexpr int D = HMI_STREAM_RING, WPB = HMI_STREAM_WPB, MINB = HMI_STREAM_MINB;
-    constexpr size_t SMEM = (size_t)WPB * (TMA ? ((D * G::SLOT_T + D * 8 + 15) / 16) * 16 : D * G::SLOT);
+    constexpr size_t SMEM = (size_t)WPB * WarpRing<T, V, K, METHOD, D, STG>::value + (STG == 2 ? 128 : 0);
     StreamArgs<T> a = a0;
     a.nwin = (a.cols + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
-    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM, TMA>;
+    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM, STG>;
     static int cta_slots = 0;         // per instantiation: CTAs resident on the whole GPU at once
     if (cta_slots == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -552,6 +622,8 @@ int stream_auto_chunk_rows(int nrows, int nwin, int halo)
 
 int stream_halo(int method, int k) { return k * method_radius(method); }
 
+int stream_cells_per_lane(int dtype, int vec) { return dtype == HMI_F32 ? 4 : (vec == 4 ? 4 : 2); }
+
 int stream_max_k(int method, int dtype)
 {
     (void)dtype;
@@ -568,7 +640,7 @@ int stream_max_blocks(int method, int rows_total, int cols)
     return (int)((nwin * nch + 3) / 4 + 1);
 }
 
-template <typename T, int V, bool TMA>
+template <typename T, int V, int TMA>
 static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
 {
     if (a.do_norm) {   // the convergence sums are fused into single-sweep launches only
@@ -590,16 +662,18 @@ static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStrea
 template <>
 cudaError_t launch_stream<float>(int method, int k, const StreamArgs<float> &a, cudaStream_t st, int *nblocks_out)
 {
-    if (a.tma) return launch_v<float, 4, true>(method, k, a, st, nblocks_out);
-    return launch_v<float, 4, false>(method, k, a, st, nblocks_out);
+    if (a.tma == 2) return launch_v<float, 4, 2>(method, k, a, st, nblocks_out);
+    if (a.tma == 1) return launch_v<float, 4, 1>(method, k, a, st, nblocks_out);
+    return launch_v<float, 4, 0>(method, k, a, st, nblocks_out);
 }
 
 template <>
 cudaError_t launch_stream<double>(int method, int k, const StreamArgs<double> &a, cudaStream_t st, int *nblocks_out)
 {
-    if (a.vec == 4) return launch_v<double, 4, false>(method, k, a, st, nblocks_out);
-    if (a.tma) return launch_v<double, 2, true>(method, k, a, st, nblocks_out);
-    return launch_v<double, 2, false>(method, k, a, st, nblocks_out);
+    if (a.vec == 4) return launch_v<double, 4, 0>(method, k, a, st, nblocks_out);
+    if (a.tma == 2) return launch_v<double, 2, 2>(method, k, a, st, nblocks_out);
+    if (a.tma == 1) return launch_v<double, 2, 1>(method, k, a, st, nblocks_out);
+    return launch_v<double, 2, 0>(method, k, a, st, nblocks_out);
 }
 
 }  // namespace hmi

@@ -1,6 +1,8 @@
 // Interface of the streaming temporal-blocked kernel (hmi_stream.cu).
 #pragma once
 
+#include <cuda.h>
+
 #include "hmi_common.cuh"
 
 namespace hmi {
@@ -9,7 +11,8 @@ constexpr int STREAM_MAX_K_HARMONIC = 8;
 constexpr int STREAM_MAX_K_CCST = 4;
 
 template <typename T>
-struct StreamArgs {
+struct alignas(64) StreamArgs {
+    CUtensorMap tmap_f, tmap_m;  // tma == 2: 2-D tensor maps of the whole src buffer and of the mask (boxes of 32*V x 3)
     const T *src;
     T *dst;
     const uint8_t *mask;
@@ -20,7 +23,8 @@ struct StreamArgs {
     int top_border, bottom_border;
     int chunk_rows;             // rows per warp chunk; 0 = auto (wave-aware), < 0 = legacy auto rule
     int vec;                    // cells per lane (fp64: 2 or 4; 0 = default)
-    int tma;                    // 1 = stage rows with TMA bulk copies + mbarriers instead of cp.async
+    int tma;                    // row staging: 0 = cp.async ring, 1 = 1-D bulk copies + mbarriers, 2 = 2-D tensor-map boxes
+    int phys_row0;              // tma == 2: tensor-map row of slab row 0 (= ghost_top)
     int nwin, nchunks;          // filled by the launcher
     int n_edge, nchunks_e, chunk_rows_e;   // column-edge strips: how many (listed first), their chunking
     T dt, tension, one_minus_tension;
@@ -41,5 +45,7 @@ int stream_cta_slots(const void *kernel, int threads, size_t smem);   // CTAs re
 void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, double edge_cost,
                         int *chunk_rows, int *chunk_rows_edge);                  // wave-aware (chunk_rows == 0)
 int stream_max_blocks(int method, int rows_total, int cols);
+int stream_cells_per_lane(int dtype, int vec);       // V of the instantiation launch_stream picks
+constexpr int STREAM_BOX_ROWS = 3;                   // rows per tensor-map box (tma == 2)
 
 }  // namespace hmi

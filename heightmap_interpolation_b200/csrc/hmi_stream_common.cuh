@@ -60,6 +60,12 @@ __device__ __forceinline__ float lds1(unsigned addr, float)
     asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(r) : "r"(addr));
     return r;
 }
+__device__ __forceinline__ unsigned lds16u(unsigned addr)
+{
+    unsigned short r;
+    asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(r) : "r"(addr));
+    return (unsigned)r;
+}
 __device__ __forceinline__ unsigned lds8(unsigned addr)
 {
     unsigned r;
@@ -89,6 +95,12 @@ __device__ __forceinline__ void tma_load_1d(unsigned dst_smem, const void *src, 
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one box of a 2-D tensor map (innermost coordinate first) into shared memory, completing on `bar`
+__device__ __forceinline__ void tma_load_2d(unsigned dst_smem, const void *tmap, int x, int y, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(dst_smem), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {

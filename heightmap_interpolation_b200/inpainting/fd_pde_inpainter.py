@@ -52,6 +52,7 @@ class FDPDEInpainter(ABC):
         # --- B200 back-end keywords
         self.device = kwargs.pop("device", None)
         self.devices = kwargs.pop("devices", None)
+        self.convolver.device = 0 if self.device is None else int(self.device)
         self.kernel = kwargs.pop("kernel", "auto")
         self.temporal_block = int(kwargs.pop("temporal_block", 0))
 
@@ -130,10 +131,27 @@ class FDPDEInpainter(ABC):
         """Extra numeric options of the subclass (tension / epsilon)."""
         return {}
 
-    def step_fun(self, f, mask):
-        """The reference evaluates one step function on the host (abstract hook, :406-408).  Here the
-        step functions only exist fused inside the sweep kernels; use ``sweeps(...)`` instead."""
-        raise NotImplementedError("step_fun is fused into the CUDA sweep kernels of the B200 back-end")
+    def step_fun(self, f, mask=None):
+        """One evaluation of the subclass's step function on the GPU (hmi_step_fun_host): the reference's
+        hook (:406-408).  `mask` is the work mask the reference passes to its convolvers (True = evaluate;
+        None = everywhere); the convolvers that ignore it (opencv, scipy-*) ignore it here too."""
+        import ctypes
+        from .convolver import _MASKED
+        f = np.ascontiguousarray(f)
+        if f.ndim != 2 or f.dtype not in (np.float32, np.float64):
+            raise TypeError("f must be a 2-D float32 or float64 array")
+        m8 = None
+        if mask is not None and self.convolver.method in _MASKED and not getattr(self, "convolve_in_1d", False):
+            m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+            if m8.shape != f.shape:
+                raise ValueError("mask must have the same shape as f")
+        self.term_criteria_int = self.map_term_criteria_str_to_int.get(self.term_criteria, 0)
+        params = self._make_params(f.shape[0], f.shape[1], f.dtype)
+        out = np.empty_like(f)
+        C.check(C.lib().hmi_step_fun_host(ctypes.byref(params), f.ctypes.data, f.strides[0],
+                                          None if m8 is None else m8.ctypes.data, 0 if m8 is None else m8.strides[0],
+                                          out.ctypes.data, out.strides[0]))
+        return out
 
     # ------------------------------------------------------------------ public API
     def inpaint(self, image, mask, out=None):

@@ -250,6 +250,26 @@ int64_t hmi_group_launch_count(const hmi_group *g);
 int hmi_inpaint_host_devices(const hmi_params *params, const int32_t *devices, int32_t n_devices, const void *image,
                              const uint8_t *mask, int32_t fill, double fill_value, void *out, hmi_status *status);
 
+/* One evaluation of the step function on a host array: out = step(f) where `work_mask` is non-zero
+ * (everywhere if it is NULL), the input value elsewhere.  Uses params->rows, cols, dtype, method,
+ * orientation, border, tension, epsilon, device.  With a work mask the result equals the reference's at
+ * every cell whose stencil support lies inside the mask (all unknown cells, for the dilated mask the
+ * reference passes, fd_pde_inpainter.py:293-296); outside it the reference's masked convolvers return
+ * by-products of copying, which only harmonic reproduces (the input value).
+ * Replaces: step_fun(f, mask)  sobolev_inpainter.py:15-17, ccst_inpainter.py:23-34, tv_inpainter.py:20-33,
+ * amle_inpainter.py:22-59 (the abstract hook fd_pde_inpainter.py:406-408). */
+int hmi_step_fun_host(const hmi_params *params, const void *f, size_t f_pitch_bytes, const uint8_t *work_mask,
+                      size_t mask_pitch_bytes, void *out, size_t out_pitch_bytes);
+
+/* One 3x3 filter on a host array with a convolver's orientation (+1 correlation = "opencv", -1
+ * convolution = the masked and SciPy convolvers) and border rule; evaluated where `mask` is non-zero
+ * (everywhere if NULL), copying the input elsewhere.  kernel9 = the 3x3 kernel in row-major order.
+ * Replaces: Convolver.__call__(image, kernel, mask)  inpainting/convolver.py:28-29 and the back ends
+ * :47-69 (cv2.filter2D, scipy.signal.convolve, nb_convolve_at_mask convolve_at_mask.py:39-63). */
+int hmi_convolve3x3_host(int32_t rows, int32_t cols, int32_t dtype, int32_t device, const void *image,
+                         size_t image_pitch_bytes, const double *kernel9, int32_t orientation, int32_t border,
+                         const uint8_t *mask, size_t mask_pitch_bytes, void *out, size_t out_pitch_bytes);
+
 /* Multi-GPU plumbing: device address and row pitch (bytes) of the current iterate and of the mask,
  * so the host layer can exchange ghost rows with NCCL (row 0 = first ghost row).  The addresses
  * change after every hmi_sweeps*() call (ping-pong). */

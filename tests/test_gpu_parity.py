@@ -183,7 +183,7 @@ def _problem(rows, cols, dtype, p=0.4, seed=3):
     return synthetic.zero_unknown(img, mask), mask
 
 
-@pytest.mark.parametrize("vec,tma", [(2, 0), (4, 0), (2, 1)])
+@pytest.mark.parametrize("vec,tma", [(2, 0), (4, 0), (2, 1), (2, 2)])
 @pytest.mark.parametrize("dt", ["f64", "f32"])
 @pytest.mark.parametrize("method,tb", [("harmonic", 1), ("harmonic", 2), ("harmonic", 3),
                                        ("harmonic", 4), ("harmonic", 5), ("harmonic", 8),
@@ -222,12 +222,37 @@ def test_tv_amle_stream_kernel_matches_oracle(method, conv, dt, shape, tb):
         assert err <= (1e-12 if dt == "f64" else 5e-6), (method, conv, dt, shape, chunk, err)
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("method,tb", [("harmonic", 6), ("ccst", 3), ("ccst", 1)])
+def test_row_staging_variants_are_bit_identical(method, tb, dt):
+    """cp.async ring, 1-D bulk copies and 2-D tensor-map boxes (TMA) only move rows into shared memory:
+    the results must not differ in a single bit, on a grid large enough for many interior strips, and
+    on a slab with ghost rows (tensor-map row 0 is then the first ghost row)."""
+    img, mask = _problem(900, 1300, DTYPES[dt])
+    outs = [gpu_sweeps(method, "opencv", img, mask, 2 * tb + 1, kernel="stream", tb=tb, tma=tma)[0] for tma in (0, 1, 2)]
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    o = METHOD_OPTS[method]
+    res = []
+    for tma in (0, 2):
+        p = make_params(700, 1300, DTYPES[dt], METHODS[method], orientation=1, dt=o["update_step_size"],
+                        tension=o.get("tension", 0.0), kernel=C.HMI_KERNEL_STREAM, temporal_block=tb,
+                        ghost_top=100, ghost_bottom=100)
+        with Solver(p) as s:
+            s.set_option("tma", tma)
+            s.set_problem_host(img, mask)
+            s.sweeps(tb)
+            res.append(s.get_result_host())
+    assert np.array_equal(res[0], res[1])
+    ref = oracle_sweeps(method, "opencv", img, mask, tb)
+    assert range_err(res[1], ref[100:800]) <= (1e-13 if dt == "f64" else 2e-6)
+
+
 @pytest.mark.parametrize("shape", [(64, 64), (130, 120), (97, 1031), (1031, 97), (512, 512)])
 def test_stream_kernel_shapes_and_chunking(shape):
     img, mask = _problem(shape[0], shape[1], np.float64)
     ref = oracle_sweeps("ccst", "masked", img, mask, 6)
     for chunk in (0, 8, 50, 10 ** 6):
-        for vec, tma in ((2, 0), (4, 0), (2, 1)):
+        for vec, tma in ((2, 0), (4, 0), (2, 1), (2, 2)):
             got, info = gpu_sweeps("ccst", "masked", img, mask, 6, kernel="stream", tb=2,
                                    chunk_rows=chunk, vec=vec, tma=tma)
             assert range_err(got, ref) <= 1e-13, (shape, chunk, vec, tma)

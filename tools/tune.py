@@ -76,8 +76,8 @@ def main():
                             nsw = (nsw // tb) * tb
                             ms = time_sweeps(s, nsw)
                         g = n * n * nsw / (ms * 1e-3) / 1e9
-                        print("%-8s %s %-7s tb=%d chunk=%-4d vec=%d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
-                              % (method, dt, kernel, tb, ch, sk, g, 100 * g * bpl / 6550.4, g * bpl), flush=True)
+                        print("%-8s %s %-7s tb=%d chunk=%-4d vec=%d tma=%d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
+                              % (method, dt, kernel, tb, ch, sk, a.tma, g, 100 * g * bpl / 6550.4, g * bpl), flush=True)
 
 
 if __name__ == "__main__":
