@@ -82,6 +82,8 @@ SYMBOLS = {
     "hmi_group_set_term_thres": (ctypes.c_int, [_vp, ctypes.c_double]),
     "hmi_group_get_result_host": (ctypes.c_int, [_vp, _vp, _sz]),
     "hmi_group_sync": (ctypes.c_int, [_vp]),
+    "hmi_group_set_problem_pyramid": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                     ctypes.c_int32, ctypes.POINTER(HmiBlendInfo)]),
     "hmi_group_info": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                       ctypes.POINTER(ctypes.c_int32)]),
     "hmi_group_slab": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_int32),

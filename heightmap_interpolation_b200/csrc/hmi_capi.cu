@@ -201,10 +201,11 @@ static int ensure_tmaps(hmi_solver *s, int V)
     if (!drv) return HMI_ERR_CUDA;
     if (!s->tmaps) s->tmaps = new (std::nothrow) CUtensorMap[3];
     if (!s->tmaps) return fail(HMI_ERR_CUDA, "out of host memory");
-    const cuuint32_t box[2] = {(cuuint32_t)(32 * V), (cuuint32_t)STREAM_BOX_ROWS};
     const cuuint32_t estr[2] = {1, 1};
     for (int i = 0; i < 3; ++i) {
         const bool is_mask = (i == 2);
+        // the mask box starts at the 16-byte aligned column below the strip and is 16 bytes wider (hmi_stream.cu)
+        const cuuint32_t box[2] = {(cuuint32_t)(32 * V + (is_mask ? 16 : 0)), (cuuint32_t)STREAM_BOX_ROWS};
         const cuuint64_t dims[2] = {(cuuint64_t)(is_mask ? s->mpitch : s->pitch), (cuuint64_t)s->phys_rows};
         const cuuint64_t strides[1] = {(cuuint64_t)(is_mask ? s->mpitch : s->pitch * s->elem)};
         const CUtensorMapDataType dt = is_mask ? CU_TENSOR_MAP_DATA_TYPE_UINT8

@@ -9,11 +9,13 @@
 // Per convergence check each slab's four partial sums come back to the host and are folded in slab
 // order.  Uploads and downloads run on one host thread per device.
 #include <cmath>
+#include <cstring>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include "hmi_init.cuh"
 #include "hmi_internal.cuh"
 #include "hmi_xfer.cuh"
 
@@ -104,8 +106,8 @@ int group_sweeps(hmi_group *g, long long n, bool norm, hmi_norm *out)
 
 int group_sync(hmi_group *g)
 {
-    for (int i = 0; i < g->n; ++i) {
-        const int rc = hmi::sync_solver(g->slab[i]);
+    for (hmi_solver *s : g->slab) {         // (a group whose creation failed half-way holds fewer than n slabs)
+        const int rc = hmi::sync_solver(s);
         if (rc != HMI_OK) return rc;
     }
     return HMI_OK;
@@ -258,6 +260,165 @@ int hmi_group_get_result_host(hmi_group *g, void *out, size_t out_pitch_bytes)
     });
     hmi::set_xfer_threads(6);
     return rc;
+}
+
+}  // extern "C"
+
+// ---- multigrid: the pyramid lives on the device(s) ------------------------------------------------
+
+static int enable_peer(int from, int to)
+{
+    if (from == to) return HMI_OK;
+    int can = 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, from, to));
+    if (!can) return fail(HMI_ERR_UNSUPPORTED, "device %d cannot access device %d's memory", from, to);
+    CUDA_TRY(cudaSetDevice(from));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(HMI_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", from, to, cudaGetErrorString(e));
+    cudaGetLastError();
+    return HMI_OK;
+}
+
+static int make_view(const hmi_group *g, bool mask, hmi::SlabView *v)
+{
+    if (g->n > hmi::MAX_VIEW_SLABS) return fail(HMI_ERR_UNSUPPORTED, "more than %d slabs", hmi::MAX_VIEW_SLABS);
+    v->n = g->n;
+    for (int k = 0; k < g->n; ++k) {
+        const hmi_solver *s = g->slab[k];
+        v->row0[k] = g->r0[k];
+        v->base[k] = mask ? (const char *)s->mask + (size_t)s->p.ghost_top * s->mpitch
+                          : (const char *)s->buf[s->cur] + (size_t)s->p.ghost_top * s->pitch * s->elem;
+    }
+    v->row0[g->n] = g->p.rows;
+    v->pitch = mask ? g->slab[0]->mpitch : g->slab[0]->pitch * g->slab[0]->elem;
+    return HMI_OK;
+}
+
+template <typename T>
+static int pyramid_slab(hmi_solver *s, int row_first, int level_rows, int stride, int scrub_nan, const hmi::SlabView &fimg,
+                        const hmi::SlabView &fmask, const hmi::SlabView &coarse, const int32_t *sx, const int32_t *sx1,
+                        const void *ax0, const void *ax1, const int32_t *sy, const int32_t *sy1, const void *by0,
+                        const void *by1, double *lo, double *hi, double *nanv, int *had_nan)
+{
+    const int cols = s->p.cols;
+    const size_t n_int = 2 * (size_t)cols + 2 * (size_t)level_rows;
+    const size_t off_val = (n_int * sizeof(int) + 15) / 16 * 16;
+    const size_t off_part = (off_val + n_int * sizeof(T) + 15) / 16 * 16;
+    const int max_blocks = hmi::upsample_max_blocks(cols);
+    const size_t off_flag = off_part + (size_t)max_blocks * 3 * sizeof(double);
+    const size_t total = off_flag + 16;
+    CUDA_TRY(cudaSetDevice(s->p.device));
+    char *d = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&d, total));
+    std::vector<char> h(off_part);
+    int *hi_ = reinterpret_cast<int *>(h.data());
+    memcpy(hi_, sx, cols * sizeof(int));
+    memcpy(hi_ + cols, sx1, cols * sizeof(int));
+    memcpy(hi_ + 2 * cols, sy, level_rows * sizeof(int));
+    memcpy(hi_ + 2 * cols + level_rows, sy1, level_rows * sizeof(int));
+    T *hv = reinterpret_cast<T *>(h.data() + off_val);
+    memcpy(hv, ax0, cols * sizeof(T));
+    memcpy(hv + cols, ax1, cols * sizeof(T));
+    memcpy(hv + 2 * cols, by0, level_rows * sizeof(T));
+    memcpy(hv + 2 * cols + level_rows, by1, level_rows * sizeof(T));
+    cudaError_t e = cudaMemcpyAsync(d, h.data(), off_part, cudaMemcpyHostToDevice, s->own);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d + off_flag, 0, 16, s->own);
+    int nblocks = 0;
+    if (e == cudaSuccess) {
+        hmi::PyramidBlend<T> a;
+        s->cur = 0;
+        a.f = (T *)s->buf[0];
+        a.mask = s->mask;
+        a.pitch = s->pitch; a.mpitch = s->mpitch;
+        a.phys_rows = s->phys_rows; a.cols = cols;
+        a.row_first = row_first;
+        a.stride = stride; a.scrub_nan = scrub_nan;
+        a.fine_img = fimg; a.fine_mask = fmask; a.coarse = coarse;
+        const int *di = reinterpret_cast<const int *>(d);
+        const T *dv = reinterpret_cast<const T *>(d + off_val);
+        a.sx = di; a.sx1 = di + cols; a.sy = di + 2 * cols; a.sy1 = di + 2 * cols + level_rows;
+        a.ax0 = dv; a.ax1 = dv + cols; a.by0 = dv + 2 * cols; a.by1 = dv + 2 * cols + level_rows;
+        a.partials = reinterpret_cast<double *>(d + off_part);
+        a.nan_flag = reinterpret_cast<int *>(d + off_flag);
+        e = hmi::launch_pyramid_blend<T>(a, &nblocks, s->own);
+    }
+    std::vector<double> part;
+    int flag = 0;
+    if (e == cudaSuccess) {
+        part.resize((size_t)nblocks * 3);
+        e = cudaMemcpyAsync(part.data(), d + off_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, s->own);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d + off_flag, sizeof(int), cudaMemcpyDeviceToHost, s->own);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->own);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HMI_ERR_CUDA, "multigrid level transition failed: %s", cudaGetErrorString(e));
+    }
+    for (int b = 0; b < nblocks; ++b) {
+        *lo = part[3 * b] < *lo ? part[3 * b] : *lo;
+        *hi = part[3 * b + 1] > *hi ? part[3 * b + 1] : *hi;
+        *nanv = part[3 * b + 2] > *nanv ? part[3 * b + 2] : *nanv;
+    }
+    *had_nan |= flag;
+    s->has_problem = true;
+    s->halo_state = 0;              // ghost rows were computed like every other row of the level
+    s->last_main = s->own;
+    return HMI_OK;
+}
+
+extern "C" {
+
+int hmi_group_set_problem_pyramid(hmi_group *level, hmi_group *finest, int32_t stride, hmi_group *coarse,
+                                  const int32_t *sx, const int32_t *sx1, const void *ax0, const void *ax1,
+                                  const int32_t *sy, const int32_t *sy1, const void *by0, const void *by1,
+                                  int32_t scrub_nan, hmi_blend_info *info)
+{
+    if (!level || !finest || !coarse || !sx || !sx1 || !ax0 || !ax1 || !sy || !sy1 || !by0 || !by1 || !info)
+        return fail(HMI_ERR_BAD_ARG, "null argument");
+    if (level == coarse) return fail(HMI_ERR_BAD_ARG, "a level cannot be its own coarser level");
+    if (stride < 1) return fail(HMI_ERR_BAD_ARG, "stride must be >= 1");
+    if ((stride == 1) != (level == finest)) return fail(HMI_ERR_BAD_ARG, "stride 1 means the finest level itself, in place");
+    if (level->p.dtype != finest->p.dtype || level->p.dtype != coarse->p.dtype)
+        return fail(HMI_ERR_BAD_ARG, "all levels must share the dtype");
+    if (!finest->has_problem) return fail(HMI_ERR_STATE, "the finest level has not been loaded");
+    if (!coarse->has_problem) return fail(HMI_ERR_STATE, "the coarser level has no solution yet");
+    const int want_rows = (finest->p.rows + stride - 1) / stride, want_cols = (finest->p.cols + stride - 1) / stride;
+    if (level->p.rows != want_rows || level->p.cols != want_cols)
+        return fail(HMI_ERR_BAD_ARG, "a stride-%d level of a %dx%d grid is %dx%d, not %dx%d", stride, finest->p.rows,
+                    finest->p.cols, want_rows, want_cols, level->p.rows, level->p.cols);
+    int rc = group_sync(finest);
+    if (rc == HMI_OK) rc = group_sync(coarse);
+    if (rc == HMI_OK) rc = group_sync(level);
+    if (rc != HMI_OK) return rc;
+    for (int i = 0; i < level->n && rc == HMI_OK; ++i) {
+        for (int k = 0; k < finest->n && rc == HMI_OK; ++k) rc = enable_peer(level->devices[i], finest->devices[k]);
+        for (int k = 0; k < coarse->n && rc == HMI_OK; ++k) rc = enable_peer(level->devices[i], coarse->devices[k]);
+    }
+    hmi::SlabView vimg, vmask, vcoarse;
+    if (rc == HMI_OK) rc = make_view(finest, false, &vimg);
+    if (rc == HMI_OK) rc = make_view(finest, true, &vmask);
+    if (rc == HMI_OK) rc = make_view(coarse, false, &vcoarse);
+    if (rc != HMI_OK) return rc;
+    double lo = INFINITY, hi = -INFINITY, nanv = 0.0;
+    int had_nan = 0;
+    for (int i = 0; i < level->n; ++i) {
+        hmi_solver *s = level->slab[i];
+        const int row_first = level->r0[i] - s->p.ghost_top;
+        rc = level->p.dtype == HMI_F64
+                 ? pyramid_slab<double>(s, row_first, level->p.rows, stride, scrub_nan, vimg, vmask, vcoarse, sx, sx1, ax0, ax1,
+                                        sy, sy1, by0, by1, &lo, &hi, &nanv, &had_nan)
+                 : pyramid_slab<float>(s, row_first, level->p.rows, stride, scrub_nan, vimg, vmask, vcoarse, sx, sx1, ax0, ax1,
+                                       sy, sy1, by0, by1, &lo, &hi, &nanv, &had_nan);
+        if (rc != HMI_OK) return rc;
+    }
+    level->has_problem = true;
+    info->min = nanv != 0.0 ? nan("") : lo;      // np.min / np.max propagate NaN
+    info->max = nanv != 0.0 ? nan("") : hi;
+    info->has_nan = nanv != 0.0 ? 1 : 0;
+    info->image_had_nan = had_nan;
+    return HMI_OK;
 }
 
 int hmi_group_info(const hmi_group *g, int32_t *n_slabs, int32_t *exchange_every, int32_t *ghost_rows)

@@ -75,7 +75,12 @@ struct Geo {
     // the wait sits in phase 0 and the refill in phase 2 with no run-time row counter.
     static constexpr int RB = 3, NBX = 4;
     static constexpr int FBOX = RB * ROW_BYTES;
-    static constexpr int MBOX = ((RB * 32 * V + 127) / 128) * 128;
+    // a box must start on a 16-byte boundary in global memory (measured: an odd start faults with "illegal
+    // instruction", tools/probes/tma2d_probe.cu); strips start at even columns, which is enough for the
+    // cells but not for the 1-byte mask, so the mask box starts at the 16-aligned column below x0 and is
+    // 16 bytes wider
+    static constexpr int MROW = 32 * V + 16;
+    static constexpr int MBOX = ((RB * MROW + 127) / 128) * 128;
     static constexpr int RING_T2 = ((NBX * (FBOX + MBOX) + NBX * 8 + 127) / 128) * 128;
     static_assert(V % N == 0 && NCH >= 1, "a lane moves whole 16-byte chunks");
     static_assert(V == 2 || V == 4, "a lane's mask bytes must sit inside one aligned 4-byte word");
@@ -118,7 +123,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     constexpr bool CC = (METHOD == HMI_CCST);
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int SK = G::SK, LAG = G::LAG;
-    constexpr int RB = G::RB, NBX = G::NBX, FBOX = G::FBOX, MBOX = G::MBOX;
+    constexpr int RB = G::RB, NBX = G::NBX, FBOX = G::FBOX, MBOX = G::MBOX, MROW = G::MROW;
     static_assert(!T2 || MODE == 0, "tensor-map boxes serve interior strips only");
     static_assert((LAG + 1) * V <= 64, "mask history does not fit 64 bits");
     static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
@@ -202,9 +207,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         if (ybox < yend && lane == 0) {
             const unsigned bar = t2_bar + 8 * slot;
             fence_proxy_async();                   // the slot's previous contents were read with ld.shared
-            mbar_expect_tx(bar, (unsigned)(FBOX + RB * 32 * V));
+            mbar_expect_tx(bar, (unsigned)(FBOX + RB * MROW));
             tma_load_2d(t2_f + slot * FBOX, &a.tmap_f, x0, ybox + a.phys_row0, bar);
-            tma_load_2d(t2_m + slot * MBOX, &a.tmap_m, x0, ybox + a.phys_row0, bar);
+            tma_load_2d(t2_m + slot * MBOX, &a.tmap_m, x0 & ~15, ybox + a.phys_row0, bar);
         }
     };
     if (T2) {
@@ -299,8 +304,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         // mask bytes are 0/1: one multiply packs them into V bits, cell v -> bit V-1-v
         unsigned mb;
         if (T2) {
-            // the box starts at column x0, so this lane's V mask bytes sit at byte V*lane of the row
-            const unsigned ma = t2_m + t2_slot * MBOX + PH * (32 * V) + lane * V;
+            // the mask box starts at column x0 & ~15, so this lane's V mask bytes sit at byte (x0 & 15) + V*lane of the row
+            const unsigned ma = t2_m + t2_slot * MBOX + PH * MROW + (unsigned)(x0 & 15) + lane * V;
             if (V == 4) mb = (lds32(ma) * 0x08040201u) >> 24;
             else mb = ((lds16u(ma) * 0x0201u) >> 8) & 3u;
             if (PH == 2) {                         // last row of the box: refill its slot with box t2_box + NBX

@@ -251,6 +251,24 @@ class Group:
     def fill_unknown(self, value):
         C.check(self._lib.hmi_group_fill_unknown(self._h, float(value)))
 
+    def set_problem_pyramid(self, finest, stride, coarse, xtab, ytab, scrub_nan=False):
+        """Multigrid: make this group pyramid level log2(stride) of the problem `finest` holds — image and mask
+        gathered from it on the device, unknown cells <- the up-sampled current iterate of `coarse`
+        (hmi_group_set_problem_pyramid).  stride 1: `finest` itself, in place.  xtab / ytab are the
+        (src0, src1, w0, w1) tables of cv2's INTER_LINEAR per axis.  Returns HmiBlendInfo."""
+        p = self.params
+        tabs = []
+        for (s0, s1, w0, w1), n in ((xtab, p.cols), (ytab, p.rows)):
+            tabs += [np.ascontiguousarray(s0, dtype=np.int32), np.ascontiguousarray(s1, dtype=np.int32),
+                     np.ascontiguousarray(w0, dtype=self.np_dtype), np.ascontiguousarray(w1, dtype=self.np_dtype)]
+            if any(t.shape != (n,) for t in tabs[-4:]):
+                raise ValueError("interpolation tables must have one entry per output column / row")
+        info = C.HmiBlendInfo()
+        C.check(self._lib.hmi_group_set_problem_pyramid(self._h, finest._h, int(stride), coarse._h,
+                                                        *[t.ctypes.data for t in tabs], 1 if scrub_nan else 0,
+                                                        ctypes.byref(info)))
+        return info
+
     def sweeps(self, n):
         C.check(self._lib.hmi_group_sweeps(self._h, int(n)))
 

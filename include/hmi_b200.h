@@ -242,6 +242,19 @@ int hmi_group_run(hmi_group *g, hmi_status *status);         /* FDPDEInpainter.i
 int hmi_group_set_term_thres(hmi_group *g, double term_thres);
 int hmi_group_get_result_host(hmi_group *g, void *out, size_t out_pitch_bytes);
 int hmi_group_sync(hmi_group *g);
+/* Multigrid with the pyramid on the device(s) (FDPDEInpainter.inpaint_multigrid, fd_pde_inpainter.py:187-279):
+ * load pyramid level l = log2(stride) into `level` without touching the host again.  `finest` holds the
+ * full-resolution image and mask (hmi_group_set_problem_host); level l is every stride-th cell of it
+ * (halve_image applied l times, misc/image_proc.py:4-12) with the mask ANDed with "image is not NaN"
+ * (:223-224); its unknown cells take cv2.resize(current iterate of `coarse`) and its known cells the image,
+ * by the reference's arithmetic blend (:255-263; taps and weights as for hmi_set_problem_host_blend, sy /
+ * by* indexed by the level's global row).  stride 1 blends `finest` itself in place (level == finest), with
+ * scrub_nan as at level 0 (:259-260).  The three groups may use different device lists; rows are read
+ * across GPUs through peer memory. */
+int hmi_group_set_problem_pyramid(hmi_group *level, hmi_group *finest, int32_t stride, hmi_group *coarse,
+                                  const int32_t *sx, const int32_t *sx1, const void *ax0, const void *ax1,
+                                  const int32_t *sy, const int32_t *sy1, const void *by0, const void *by1,
+                                  int32_t scrub_nan, hmi_blend_info *info);
 int hmi_group_info(const hmi_group *g, int32_t *n_slabs, int32_t *exchange_every, int32_t *ghost_rows);
 int hmi_group_slab(hmi_group *g, int32_t i, hmi_solver **solver, int32_t *row0, int32_t *row1);
 int64_t hmi_group_launch_count(const hmi_group *g);

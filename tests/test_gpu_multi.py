@@ -237,3 +237,46 @@ def test_one_process_per_gpu_slabs_bit_identical_to_one_gpu(halo):
         assert all(p[3] == one.iterations_ for p in parts), (key, [p[3] for p in parts], one.iterations_)
         assert parts[0][4] > 0
         assert np.array_equal(got, want), (key, halo, range_err(got, want))
+
+
+# ------------------------------------------------------------------ multigrid with the pyramid on the device(s)
+@pytest.mark.parametrize("method,dt,crit,init", [("harmonic", np.float64, "absolute_percent", "mean"),
+                                                 ("ccst", np.float32, "relative", "zeros"),
+                                                 ("tv", np.float64, "relative", "nearest")])
+def test_multigrid_on_device_groups_equals_one_gpu_and_oracle(method, dt, crit, init):
+    """Every pyramid level is a device group: decimation from one upload, up-sampling of the coarser
+    solution across slabs (peer reads), blend, z-range — bit-identical to the single-GPU run, same
+    per-level iteration counts as the oracle's restatement of inpaint_multigrid (fp64: 1e-10)."""
+    rows, cols = 333, 470                     # odd sizes at every level
+    mask = synthetic.mask_holes((rows, cols), 12, 25, seed=4) & synthetic.mask_random((rows, cols), 0.2, seed=5)
+    img = synthetic.bathymetry((rows, cols), dtype=dt)
+    img[~mask] = np.nan                       # level 0 scrubs them (:259-260); the coarsest initialiser writes through
+    opts = dict(METHOD_OPTS[method], convolver="opencv", term_criteria=crit, term_thres=1e-5 if dt == np.float64 else 1e-4,
+                term_check_iters=20, max_iters=3000, mgs_levels=3, mgs_min_res=50, init_with=init)
+    one = CLASSES[method](**opts)
+    a = img.copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        want = one.inpaint(a, mask)
+    assert len(one.history_) == 3 and not np.isnan(want).any()
+    for devs in device_lists():
+        inp = CLASSES[method](devices=devs, **opts)
+        b = img.copy()
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = inp.inpaint(b, mask)
+        assert inp.history_ == one.history_, (devs, inp.history_, one.history_)
+        assert np.array_equal(got, want), (method, devs, range_err(got, want))
+        assert np.array_equal(a, b, equal_nan=True)
+        assert float(inp.term_thres) == float(one.term_thres)
+    if init != "nearest":
+        src = img.copy()
+        src[~mask] = 0                        # the oracle's blend has no NaN scrub of its own at level 0
+        ora = OracleInpainter(method, **opts)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref = ora.inpaint(src, mask)
+        c = img.copy()
+        c[~mask] = 0
+        chk = CLASSES[method](**opts)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got0 = chk.inpaint(c, mask)
+        assert chk.history_ == ora.history
+        assert range_err(got0, ref) <= (1e-10 if dt == np.float64 else 1e-5)

@@ -269,7 +269,7 @@ def test_host_loop_check_cadence():
 
 def test_bilinear_resize_matches_opencv():
     cv2 = pytest.importorskip("cv2")
-    from heightmap_interpolation_b200.inpainting.multigrid import halve_image, resize_bilinear
+    from heightmap_interpolation_b200.inpainting.multigrid import pyramid_shapes, resize_bilinear
     rng = np.random.default_rng(0)
     for dt, tol in ((np.float64, 1e-13), (np.float32, 1e-6)):
         for sh, dh in (((50, 64), (100, 128)), ((51, 66), (101, 131)), ((26, 33), (51, 66)), ((37, 53), (74, 105))):
@@ -278,9 +278,12 @@ def test_bilinear_resize_matches_opencv():
             got = resize_bilinear(src, dh[0], dh[1])
             assert got.dtype == want.dtype
             assert np.abs(got - want).max() <= tol * 300
+    # pyramid geometry: ceil-halving per level (= every 2**l-th cell), stopping before a level below min_res
+    assert pyramid_shapes((5, 7), 3, 1) == ([(5, 7), (3, 4), (2, 2)], None)
+    assert pyramid_shapes((401, 300), 4, 100) == ([(401, 300), (201, 150)], 2)
+    assert pyramid_shapes((64, 64), 1, 100) == ([(64, 64)], None)
     a = np.arange(35.0).reshape(5, 7)
-    h = halve_image(a)
-    assert h.shape == (3, 4) and h.base is not None and h[1, 1] == a[2, 2]      # a view, like the reference
+    assert a[::4, ::4].shape == pyramid_shapes((5, 7), 3, 1)[0][2]
 
 
 def test_inpaint_work_areas_crop_and_paste():
