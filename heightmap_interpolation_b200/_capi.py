@@ -49,6 +49,11 @@ class HmiHaloInfo(ctypes.Structure):
                 ("reserved", ctypes.c_int32), ("ipc_handle", ctypes.c_ubyte * 64)]
 
 
+class HmiWindowInfo(ctypes.Structure):
+    _fields_ = [("known", ctypes.c_int64), ("unknown", ctypes.c_int64), ("known_sum", ctypes.c_double),
+                ("known_min", ctypes.c_double), ("known_max", ctypes.c_double)]
+
+
 class HmiNorm(ctypes.Structure):
     _fields_ = [("sum_d2", ctypes.c_double), ("sum_f2", ctypes.c_double),
                 ("max_abs", ctypes.c_double), ("has_nan", ctypes.c_double)]
@@ -107,6 +112,13 @@ SYMBOLS = {
     "hmi_convolve3x3_host": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _sz,
                                             ctypes.POINTER(ctypes.c_double), ctypes.c_int32, ctypes.c_int32, _vp, _sz,
                                             _vp, _sz]),
+    "hmi_areas_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _sz, _vp, _sz,
+                                        ctypes.POINTER(_vp)]),
+    "hmi_areas_destroy": (None, [_vp]),
+    "hmi_areas_set_work_area": (ctypes.c_int, [_vp, _vp, _sz]),
+    "hmi_areas_load_window": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(HmiWindowInfo)]),
+    "hmi_areas_paste": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32]),
+    "hmi_areas_get_result_host": (ctypes.c_int, [_vp, _vp, _sz]),
     "hmi_current_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_mask_grid": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_sz)]),
     "hmi_host_fill_unknown": (ctypes.c_int, [_vp, _vp, _i64, ctypes.c_int32, ctypes.c_double]),

@@ -19,18 +19,6 @@
 #include "hmi_internal.cuh"
 #include "hmi_xfer.cuh"
 
-struct hmi_group {
-    hmi_params p;                       // the whole grid (rows = global rows, ghost_* = 0)
-    int n = 0;
-    int radius = 1;
-    int exchange_every = 1;             // sweeps between halo exchanges
-    int ghost = 0;                      // radius * exchange_every
-    std::vector<int> devices;
-    std::vector<hmi_solver *> slab;
-    std::vector<int> r0, r1;            // global interior rows [r0, r1) of each slab
-    bool has_problem = false;
-};
-
 using hmi::fail;
 
 namespace {

@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "hmi_common.cuh"
 
 namespace hmi {
@@ -88,6 +90,19 @@ struct hmi_solver {
     bool linked = false;
     CUtensorMap *tmaps = nullptr;   // host copies of the tensor maps of buf[0], buf[1], mask (tma == 2)
     int tmaps_v = 0;                // cells per lane they were encoded for
+};
+
+// One grid cut into row slabs over several devices of this process (hmi_group.cu)
+struct hmi_group {
+    hmi_params p;                       // the whole grid (rows = global rows, ghost_* = 0)
+    int n = 0;
+    int radius = 1;
+    int exchange_every = 1;             // sweeps between halo exchanges
+    int ghost = 0;                      // radius * exchange_every
+    std::vector<int> devices;
+    std::vector<hmi_solver *> slab;
+    std::vector<int> r0, r1;            // global interior rows [r0, r1) of each slab
+    bool has_problem = false;
 };
 
 namespace hmi {

@@ -273,6 +273,49 @@ class FDPDEInpainter(ABC):
             return inpaint_host_devices(params, devs, image, mask, out, fill=fill, init_host=init_host)
         return inpaint_host(params, image, mask, out, fill=fill, init_host=init_host)
 
+    # -- the CLI's per-area solve with the grid resident on the device (apps/interpolate.py)
+    def can_inpaint_window(self):
+        """Initialisers that exist on the device (the others need the host: initializer.py:19-41)."""
+        return (self.init_with.lower() in ("zeros", "mean") and self.mgs_levels <= 1 and self.term_check_iters > 0)
+
+    def inpaint_window(self, session, r0, c0, rows, cols):
+        """inpaint() of the window [r0, r0 + rows) x [c0, c0 + cols) of an AreaSession: crop, known mask, NaN -> 0,
+        initialiser, solve and paste of the inpainted cells all happen on the device.  Same loop semantics and
+        thresholds as inpaint() on the cropped arrays (the 'mean' fill value is accumulated in double)."""
+        self.print_msg("*** INPAINTING ***")
+        self.history_ = []
+        self.print_msg("* Initializing the inpainting problem using the '{:s}' filler".format(self.init_with))
+        self.term_criteria_int = self.map_term_criteria_str_to_int.get(self.term_criteria, -1)
+        if self.term_criteria_int < 0:
+            raise ValueError("Unknown termination criteria!")
+        dtype = session.np_dtype
+        params = self._make_params(rows, cols, dtype, term_thres=self.term_thres if self.term_thres > 0 else 1.0)
+        devs = self._device_list() or [self._device()]
+        with Group(params, devs) as g:
+            info = session.load_window(g, r0, c0)
+            if self.init_with.lower() == "zeros":
+                value = 0.0
+            else:
+                value = float(dtype(info.known_sum / info.known)) if info.known else float("nan")
+            lo, hi = info.known_min, info.known_max
+            if info.unknown and value == value:
+                lo, hi = (min(lo, value), max(hi, value)) if info.known else (value, value)
+            self.set_term_criteria(_RangeView(dtype(lo), dtype(hi)))
+            g.set_term_thres(self.term_thres)
+            params.term_thres = float(self.term_thres)
+            g.fill_unknown(value)
+            self.print_msg("* Optimization:")
+            if self.print_progress:
+                done, diff, conv = self._loop(g, params.criteria)
+            else:
+                st = g.run()
+                done, diff, conv = st.updates_done, st.last_diff, bool(st.converged)
+            self._record(done, diff, conv, g.kernel_name, g.launch_count)
+            self.history_.append((rows, cols, self.iterations_))
+            if not self.converged_:
+                print("[WARNING] Inpainting did NOT converge: Maximum number of iterations reached...")
+            session.paste(g, r0, c0)
+
     def _record(self, done, diff, conv, kernel_name, launches):
         self.iterations_, self.last_diff_, self.converged_ = int(done), float(diff), bool(conv)
         self.kernel_name_, self.launches_ = kernel_name, launches

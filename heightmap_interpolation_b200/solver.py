@@ -319,6 +319,69 @@ class Group:
         return self._lib.hmi_temporal_block(h)
 
 
+class AreaSession:
+    """The elevation grid, mask_int and elevation_int resident on one GPU for the reference CLI's loop over
+    work areas (hmi_areas_*): windows are cropped, masked, NaN-scrubbed and pasted back on the device."""
+
+    def __init__(self, elevation, mask_int, device=0):
+        self._lib = C.lib()
+        self.elevation = np.ascontiguousarray(elevation)
+        if self.elevation.dtype not in (np.float32, np.float64) or self.elevation.ndim != 2:
+            raise TypeError("elevation must be a 2-D float32 or float64 array")
+        self.np_dtype = self.elevation.dtype.type
+        m8 = np.ascontiguousarray(mask_int, dtype=bool).view(np.uint8)
+        if m8.shape != self.elevation.shape:
+            raise ValueError("elevation and mask_int must have the same shape")
+        h = ctypes.c_void_p()
+        C.check(self._lib.hmi_areas_create(self.elevation.shape[0], self.elevation.shape[1], dtype_code(self.elevation.dtype),
+                                           int(device), self.elevation.ctypes.data, self.elevation.strides[0],
+                                           m8.ctypes.data, m8.strides[0], ctypes.byref(h)))
+        self._h = h
+        self.shape = self.elevation.shape
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hmi_areas_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_work_area(self, area):
+        """`area`: bool layer of the grid's shape, or None for one area covering the grid."""
+        if area is None:
+            C.check(self._lib.hmi_areas_set_work_area(self._h, None, 0))
+            return
+        a8 = np.ascontiguousarray(area, dtype=bool).view(np.uint8)
+        if a8.shape != self.shape:
+            raise ValueError("work area must have the grid's shape")
+        C.check(self._lib.hmi_areas_set_work_area(self._h, a8.ctypes.data, a8.strides[0]))
+
+    def load_window(self, group, r0, c0):
+        info = C.HmiWindowInfo()
+        C.check(self._lib.hmi_areas_load_window(self._h, group._h, int(r0), int(c0), ctypes.byref(info)))
+        return info
+
+    def paste(self, group, r0, c0):
+        C.check(self._lib.hmi_areas_paste(self._h, group._h, int(r0), int(c0)))
+
+    def result(self):
+        out = np.empty(self.shape, dtype=self.np_dtype)
+        if out.nbytes >= (1 << 22):
+            self._lib.hmi_host_prefault(out.ctypes.data, out.nbytes)
+        C.check(self._lib.hmi_areas_get_result_host(self._h, out.ctypes.data, out.strides[0]))
+        return out
+
+
 def inpaint_host_devices(params, devices, image, mask, out=None, fill=None, init_host=False):
     """hmi_inpaint_host_devices: the one-shot call over several GPUs of this process."""
     lib = C.lib()

@@ -283,6 +283,29 @@ int hmi_convolve3x3_host(int32_t rows, int32_t cols, int32_t dtype, int32_t devi
                          size_t image_pitch_bytes, const double *kernel9, int32_t orientation, int32_t border,
                          const uint8_t *mask, size_t mask_pitch_bytes, void *out, size_t out_pitch_bytes);
 
+/* The gridded branch of the reference CLI with the grid resident on the device
+ * (interpolate(), apps/interpolate_netcdf4.py:176-212; same code in apps/interpolate_xyz.py:255-279).
+ * hmi_areas_create uploads `elevation` and `mask_int` (non-zero = cell to interpolate) once and keeps
+ * elevation_int = copy(elevation) on the device (:56).  Per work area: hmi_areas_set_work_area uploads the
+ * area's layer (NULL = one area covering the grid, netcdf_data_io.py:262); hmi_areas_load_window builds the
+ * window problem [r0, r0 + rows) x [c0, c0 + cols) (the sizes of `g`) straight into the group's slabs —
+ * crop (:187-188), known = ~mask_int | ~area (:187-190), NaN -> 0 (:192) — and returns the count, sum, minimum
+ * and maximum of the known cells (what the 'mean' initialiser and the 'absolute_percent' z-range need);
+ * after the solve hmi_areas_paste writes the inpainted cells, and only those, into elevation_int
+ * (:210-212); hmi_areas_get_result_host downloads elevation_int. */
+typedef struct hmi_areas hmi_areas;
+typedef struct hmi_window_info {
+    int64_t known, unknown;
+    double known_sum, known_min, known_max;
+} hmi_window_info;
+int hmi_areas_create(int32_t rows, int32_t cols, int32_t dtype, int32_t device, const void *elevation,
+                     size_t elevation_pitch_bytes, const uint8_t *mask_int, size_t mask_pitch_bytes, hmi_areas **out);
+void hmi_areas_destroy(hmi_areas *a);
+int hmi_areas_set_work_area(hmi_areas *a, const uint8_t *work_area, size_t pitch_bytes);
+int hmi_areas_load_window(hmi_areas *a, hmi_group *g, int32_t r0, int32_t c0, hmi_window_info *info);
+int hmi_areas_paste(hmi_areas *a, hmi_group *g, int32_t r0, int32_t c0);
+int hmi_areas_get_result_host(hmi_areas *a, void *elevation_int, size_t pitch_bytes);
+
 /* Multi-GPU plumbing: device address and row pitch (bytes) of the current iterate and of the mask,
  * so the host layer can exchange ghost rows with NCCL (row 0 = first ghost row).  The addresses
  * change after every hmi_sweeps*() call (ping-pong). */

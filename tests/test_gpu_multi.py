@@ -240,24 +240,29 @@ def test_one_process_per_gpu_slabs_bit_identical_to_one_gpu(halo):
 
 
 # ------------------------------------------------------------------ multigrid with the pyramid on the device(s)
-@pytest.mark.parametrize("method,dt,crit,init", [("harmonic", np.float64, "absolute_percent", "mean"),
-                                                 ("ccst", np.float32, "relative", "zeros"),
-                                                 ("tv", np.float64, "relative", "nearest")])
-def test_multigrid_on_device_groups_equals_one_gpu_and_oracle(method, dt, crit, init):
+@pytest.mark.parametrize("method,dt,crit,init,levels,nans", [("harmonic", np.float64, "absolute_percent", "mean", 3, False),
+                                                             ("ccst", np.float32, "relative", "zeros", 3, False),
+                                                             ("tv", np.float64, "relative", "nearest", 3, False),
+                                                             ("harmonic", np.float32, "relative", "mean", 2, True),
+                                                             ("ccst", np.float64, "absolute_percent", "zeros", 2, True)])
+def test_multigrid_on_device_groups_equals_one_gpu_and_oracle(method, dt, crit, init, levels, nans):
     """Every pyramid level is a device group: decimation from one upload, up-sampling of the coarser
     solution across slabs (peer reads), blend, z-range — bit-identical to the single-GPU run, same
-    per-level iteration counts as the oracle's restatement of inpaint_multigrid (fp64: 1e-10)."""
+    per-level iteration counts as the oracle's restatement of inpaint_multigrid (fp64: 1e-10).  With NaNs
+    in the unknown cells (two levels: an intermediate level would be poisoned by NaN * 0, in the reference
+    too) the coarsest initialiser writes through the strided view and level 0 scrubs the rest (:259-260)."""
     rows, cols = 333, 470                     # odd sizes at every level
     mask = synthetic.mask_holes((rows, cols), 12, 25, seed=4) & synthetic.mask_random((rows, cols), 0.2, seed=5)
     img = synthetic.bathymetry((rows, cols), dtype=dt)
-    img[~mask] = np.nan                       # level 0 scrubs them (:259-260); the coarsest initialiser writes through
+    img[~mask] = np.nan if nans else 0
     opts = dict(METHOD_OPTS[method], convolver="opencv", term_criteria=crit, term_thres=1e-5 if dt == np.float64 else 1e-4,
-                term_check_iters=20, max_iters=3000, mgs_levels=3, mgs_min_res=50, init_with=init)
+                term_check_iters=20, max_iters=3000, mgs_levels=levels, mgs_min_res=50, init_with=init)
     one = CLASSES[method](**opts)
     a = img.copy()
     with contextlib.redirect_stdout(io.StringIO()):
         want = one.inpaint(a, mask)
-    assert len(one.history_) == 3 and not np.isnan(want).any()
+    assert len(one.history_) == levels and not np.isnan(want).any()
+    assert not np.isnan(a).any() and np.array_equal(a[mask], img[mask])      # scrubbed / initialised in place
     for devs in device_lists():
         inp = CLASSES[method](devices=devs, **opts)
         b = img.copy()
@@ -265,18 +270,79 @@ def test_multigrid_on_device_groups_equals_one_gpu_and_oracle(method, dt, crit, 
             got = inp.inpaint(b, mask)
         assert inp.history_ == one.history_, (devs, inp.history_, one.history_)
         assert np.array_equal(got, want), (method, devs, range_err(got, want))
-        assert np.array_equal(a, b, equal_nan=True)
+        assert np.array_equal(a, b)
         assert float(inp.term_thres) == float(one.term_thres)
-    if init != "nearest":
-        src = img.copy()
-        src[~mask] = 0                        # the oracle's blend has no NaN scrub of its own at level 0
+    if init != "nearest" and not nans:
         ora = OracleInpainter(method, **opts)
         with contextlib.redirect_stdout(io.StringIO()):
-            ref = ora.inpaint(src, mask)
-        c = img.copy()
-        c[~mask] = 0
-        chk = CLASSES[method](**opts)
-        with contextlib.redirect_stdout(io.StringIO()):
-            got0 = chk.inpaint(c, mask)
-        assert chk.history_ == ora.history
-        assert range_err(got0, ref) <= (1e-10 if dt == np.float64 else 1e-5)
+            ref = ora.inpaint(img.copy(), mask)
+        assert one.history_ == ora.history
+        assert range_err(want, ref) <= (1e-10 if dt == np.float64 else 1e-5)
+
+
+# ------------------------------------------------------------------ the CLI's loop over work areas, on the device
+def _cli_case(dt):
+    rows, cols = 420, 610
+    elev = synthetic.bathymetry((rows, cols), dtype=dt)
+    mask_int = ~(synthetic.mask_holes((rows, cols), 10, 22, seed=8) & synthetic.mask_random((rows, cols), 0.25, seed=9))
+    elev[mask_int] = np.nan                                   # what a NetCDF grid with holes looks like
+    areas = np.zeros((rows, cols, 3), dtype=bool)
+    areas[30:260, 40:400, 0] = True
+    yy, xx = np.ogrid[:rows, :cols]
+    areas[:, :, 1] = (yy - 250) ** 2 + (xx - 380) ** 2 < 150 ** 2          # overlaps area 0, not a rectangle
+    areas[300:410, 5:120, 2] = True
+    return elev, mask_int, areas
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("method,init,crit", [("harmonic", "zeros", "absolute_percent"), ("ccst", "mean", "relative"),
+                                              ("tv", "zeros", "relative")])
+def test_work_areas_on_the_device_equal_the_host_route(method, init, crit, dt):
+    """inpaint_work_areas (apps/interpolate_netcdf4.py:176-212): crop, known mask, NaN -> 0, initialiser, solve
+    and paste on the device against the same loop through host arrays — several overlapping areas, NaN
+    holes, one GPU and device groups."""
+    import argparse
+    from heightmap_interpolation_b200.apps.interpolate import inpaint_work_areas
+    elev, mask_int, areas = _cli_case(dt)
+    opts = dict(METHOD_OPTS[method], convolver="opencv", term_criteria=crit, term_thres=1e-4, term_check_iters=20,
+                max_iters=200, init_with=init)
+    seen = []
+
+    def factory(devices=None):
+        def make():
+            seen.append(CLASSES[method](devices=devices, **opts))
+            return seen[-1]
+        return make
+    with contextlib.redirect_stdout(io.StringIO()):
+        host = inpaint_work_areas(elev, mask_int, areas, inpainter_factory=factory(), on_device=False)
+        host_iters = [s.iterations_ for s in seen if s.iterations_ is not None]
+        for devs in [None] + device_lists()[:2]:
+            del seen[:]
+            dev = inpaint_work_areas(elev, mask_int, areas, inpainter_factory=factory(devs), on_device=True)
+            assert [s.iterations_ for s in seen] == host_iters
+            if init == "zeros":
+                assert np.array_equal(dev, host, equal_nan=True), (method, devs)
+            else:                       # the mean is accumulated in double on the device
+                assert np.array_equal(np.isnan(dev), np.isnan(host))
+                ok = ~np.isnan(host)
+                assert np.abs(dev[ok] - host[ok]).max() <= (1e-9 if dt == np.float64 else 1e-2)
+    inside = areas.any(axis=2) & mask_int
+    assert not np.isnan(host[inside]).any()                               # every flagged cell inside an area was filled
+    assert np.isnan(host[mask_int & ~areas.any(axis=2)]).all()            # holes outside the areas stay holes
+    assert np.array_equal(host[~mask_int], elev[~mask_int])               # known cells untouched
+    # no areas = one area covering the grid; the CLI namespace route
+    ns = argparse.Namespace(subparser_name="harmonic", update_step_size=0.2, term_thres=1e-4, term_criteria="relative",
+                            term_check_iters=20, max_iters=100, relaxation=0, mgs_levels=1, mgs_min_res=100, init_with="zeros",
+                            convolver="opencv", debug_dir="", verbose=False, print_progress_iters=1000, backend="b200")
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = inpaint_work_areas(elev, mask_int, None, ns)
+        b = inpaint_work_areas(elev, mask_int, None, ns, on_device=False)
+    assert np.array_equal(a, b) and not np.isnan(a).any()
+
+
+def test_work_areas_device_route_is_refused_when_the_initialiser_needs_the_host():
+    from heightmap_interpolation_b200.apps.interpolate import inpaint_work_areas
+    elev, mask_int, areas = _cli_case(np.float64)
+    with pytest.raises(ValueError):
+        inpaint_work_areas(elev, mask_int, areas, inpainter_factory=lambda: hmi.SobolevInpainter(init_with="nearest"),
+                           on_device=True)

@@ -22,6 +22,7 @@ ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--sweeps", type=int, default=12)
 ap.add_argument("--mask", default="tracks")
 ap.add_argument("--vec", type=int, default=-1)
+ap.add_argument("--tma", type=int, default=0)
 a = ap.parse_args()
 M = {"harmonic": (C.HMI_HARMONIC, 0.2), "ccst": (C.HMI_CCST, 0.01), "tv": (C.HMI_TV, 0.225), "amle": (C.HMI_AMLE, 0.01)}
 dtype = np.float64 if a.dtype == "f64" else np.float32
@@ -36,6 +37,8 @@ with Solver(p) as s:
         s.set_option("chunk_rows", a.chunk)
     if a.vec >= 0:
         s.set_option("vec", a.vec)
+    if a.tma:
+        s.set_option("tma", a.tma)
     s.set_problem_host(img, mask)
     nm = s.sweeps_norm(a.sweeps)
     print(s.kernel_name, s.temporal_block, s.launch_count, nm.sum_d2, nm.sum_f2)
