@@ -177,6 +177,12 @@ def main():
     cases.append(("tv", "opencv", "f32", "absolute_percent", 1e-4, 10, {}))
     cases.append(("harmonic", "opencv", "f64", "relative", 1e-5, 10, {"init_with": "mean"}))
     cases.append(("harmonic", "opencv", "f64", "relative", 1e-9, 10, {"max_iters": 25}))  # not converged
+    # fp32 runs of the one-sided schemes (appended: the keys above keep their index)
+    cases.append(("amle", "opencv", "f32", "relative", 1e-4, 10, {}))
+    cases.append(("amle", "masked", "f32", "relative", 1e-4, 10, {}))
+    cases.append(("tv", "masked", "f32", "relative", 1e-4, 10, {}))
+    cases.append(("tv", "masked", "f32", "absolute_percent", 1e-3, 10, {"max_iters": 4000}))
+    cases.append(("amle", "masked", "f32", "absolute_percent", 1e-4, 10, {"max_iters": 4000}))
     for idx, (method, conv, dt_name, crit, thres, T, extra) in enumerate(cases):
         opts = dict(METHOD_OPTS[method])
         opts.update(convolver=conv, term_criteria=crit, term_thres=thres, term_check_iters=T)

@@ -170,3 +170,29 @@ def test_product_resize_equals_oracle_resize():
                                    ((7, 9), (13, 18))):
             src = rng.standard_normal((sr, sc)).astype(dt)
             assert np.array_equal(product_resize(src, dr, dc), oracle_resize(src, dr, dc))
+
+
+def test_fp32_amle_is_ill_conditioned_on_jump_data_in_the_oracle_itself():
+    """Pins the statement behind the one skipped GPU combination (test_mid_sized_odd_grids_streaming_equals_generic,
+    AMLE fp32; DESIGN.md "AMLE in fp32"): on the 1501 x 2047 bathymetry grid with 40-cell holes the CPU
+    restatement of the reference run in fp32 differs from the same restatement in fp64 by 7.5e-3 of the
+    range after 7 sweeps, at cell (861, 1097) — the direction g/|g| of amle_inpainter.py:53-57 is decided
+    by rounding noise there — while almost every other cell agrees to fp32 accuracy."""
+    from heightmap_interpolation_b200 import synthetic
+    rows, cols = 1501, 2047
+    mask = synthetic.mask_holes((rows, cols), 30, 40, seed=3) & synthetic.mask_random((rows, cols), 0.3, seed=4)
+    mask[0, :] = mask[-1, :] = False
+    mask[:, 0] = mask[:, -1] = False
+    res = {}
+    for dt in ("f64", "f32"):
+        img = synthetic.bathymetry((rows, cols), dtype=DTYPES[dt])
+        img[~mask] = 0
+        o = OracleInpainter("amle", convolver="opencv", update_step_size=0.01, max_iters=7, term_thres=1e-300,
+                            term_check_iters=10 ** 9)
+        res[dt] = o.inpaint_grid(img, mask).astype(np.float64)
+    d = np.abs(res["f64"] - res["f32"]) / float(res["f64"].max() - res["f64"].min())
+    worst = np.unravel_index(d.argmax(), d.shape)
+    assert worst == (861, 1097)
+    assert 5e-3 < d.max() < 1e-2                         # 7.52e-3: three orders above the fp32 bar of 1e-5
+    assert (d > 1e-3).sum() <= 10 and (d > 1e-5).sum() <= 2000   # 5 and 1058 cells of 3.07 million
+    assert np.median(d[~mask]) < 1e-7
