@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhmi_b200.so")
-SOURCES = ["hmi_capi.cu", "hmi_halo.cu", "hmi_group.cu", "hmi_ops.cu", "hmi_areas.cu", "hmi_generic.cu", "hmi_stream.cu", "hmi_stream_nl.cu", "hmi_init.cu",
+SOURCES = ["hmi_capi.cu", "hmi_halo.cu", "hmi_group.cu", "hmi_ops.cu", "hmi_areas.cu", "hmi_generic.cu", "hmi_stream.cu", "hmi_pipe.cu", "hmi_stream_nl.cu", "hmi_init.cu",
            "hmi_xfer.cu", "hmi_host.cpp"]
 HEADERS = ["hmi_common.cuh", "hmi_internal.cuh", "hmi_stream.cuh", "hmi_stream_nl.cuh", "hmi_stream_common.cuh", "hmi_init.cuh", "hmi_xfer.cuh", os.path.join("..", "..", "include", "hmi_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

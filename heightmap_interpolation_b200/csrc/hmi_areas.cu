@@ -148,7 +148,7 @@ int hmi_areas_create(int32_t rows, int32_t cols, int32_t dtype, int32_t device, 
     if (elevation_pitch_bytes < (size_t)cols * elem || mask_pitch_bytes < (size_t)cols)
         return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
     int ndev = 0;
-    const cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    const cudaError_t e0 = hmi::device_count_patiently(&ndev);
     if (e0 != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(HMI_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -131,6 +132,23 @@ const DriverApi *driver_api()
 
 using hmi::fail;
 using hmi::round_up;
+namespace hmi {
+// The first CUDA call of a process on a box that has just come up can fail with an initialisation
+// error while the driver is still starting (seen once on a fresh B200 box, profiles/README.md); that
+// is not "no device", so ask again a few times before giving up.
+cudaError_t device_count_patiently(int *ndev)
+{
+    cudaError_t e = cudaSuccess;
+    for (int attempt = 0; attempt < 5; ++attempt) {
+        e = cudaGetDeviceCount(ndev);
+        if (e != cudaErrorInitializationError && e != cudaErrorSystemNotReady && e != cudaErrorDevicesUnavailable) break;
+        cudaGetLastError();
+        std::this_thread::sleep_for(std::chrono::milliseconds(1000));
+    }
+    return e;
+}
+}  // namespace hmi
+
 using hmi::cached_malloc;
 using hmi::cached_free;
 
@@ -513,7 +531,7 @@ const char *hmi_last_error(void) { return hmi::g_err; }
 int hmi_device_count(void)
 {
     int n = 0;
-    const cudaError_t e = cudaGetDeviceCount(&n);
+    const cudaError_t e = hmi::device_count_patiently(&n);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(HMI_ERR_NO_DEVICE, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
@@ -548,7 +566,7 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     if (p.temporal_block < 0) return fail(HMI_ERR_BAD_ARG, "negative temporal_block");
 
     int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
+    cudaError_t e = hmi::device_count_patiently(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(HMI_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
@@ -675,12 +693,13 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
     }
     if (!strcmp(key, "tma")) {
         // 0 = cp.async ring (default), 1 = 1-D bulk copies per row, 2 = 2-D tensor-map boxes (interior strips)
-        if (value < 0 || value > 2) return fail(HMI_ERR_BAD_ARG, "tma must be 0, 1 or 2");
+        // 3 = the warp-specialised pipeline kernel (hmi_pipe.cu) for the launches that fuse >= 2 sweeps
+        if (value < 0 || value > 3) return fail(HMI_ERR_BAD_ARG, "tma must be 0, 1, 2 or 3");
         s->tma = (int)value;
         return HMI_OK;
     }
     if (!strcmp(key, "vec")) {
-        if (value != 0 && value != 2 && value != 4) return fail(HMI_ERR_BAD_ARG, "vec must be 0, 2 or 4");
+        if (value != 0 && value != 2 && value != 4 && value != 8) return fail(HMI_ERR_BAD_ARG, "vec must be 0, 2, 4 or 8");
         s->vec = (int)value;
         return HMI_OK;
     }
@@ -879,7 +898,7 @@ int hmi_init_nearest_host(void *image, size_t image_pitch_bytes, const uint8_t *
     if (image_pitch_bytes < wbytes || mask_pitch_bytes < (size_t)cols)
         return fail(HMI_ERR_BAD_ARG, "pitch smaller than a row");
     int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
+    cudaError_t e = hmi::device_count_patiently(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(HMI_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");

@@ -12,6 +12,9 @@
 
 namespace hmi {
 
+cudaError_t device_count_patiently(int *ndev);   // cudaGetDeviceCount that rides out a driver still starting (hmi_capi.cu)
+
+
 int fail(int code, const char *fmt, ...);           // records the message hmi_last_error() returns
 
 #define CUDA_TRY(expr)                                                                               \

@@ -29,7 +29,7 @@ struct DevGrid {
 int check_device(int device)
 {
     int ndev = 0;
-    const cudaError_t e = cudaGetDeviceCount(&ndev);
+    const cudaError_t e = hmi::device_count_patiently(&ndev);
     if (e != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(HMI_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");

@@ -90,22 +90,6 @@ struct Geo {
 template <bool SMALL> struct MaskHist { typedef unsigned long long type; };
 template <> struct MaskHist<true> { typedef unsigned type; };
 
-// Sum of the four neighbours of centre row b (rows above/below + lane halos).  The association
-// (up + dn) + (l + r) is invariant under mirroring either axis (IEEE addition commutes), so a ghost
-// cell loaded from its mirror cell evolves *bit for bit* like that cell through the fused sweeps and
-// the result does not depend on how the sweeps were cut into launches or slabs.
-template <typename T, int V>
-__device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], const T (&dn)[V], T bl, T br,
-                                         T (&out)[V])
-{
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const T l = (v > 0) ? b[v - 1] : bl;
-        const T r = (v < V - 1) ? b[v + 1] : br;
-        out[v] = (up[v] + dn[v]) + (l + r);
-    }
-}
-
 // One warp streams its strip down one chunk of rows.  MODE 2 = the strip touches a grid edge (ghost
 // columns to mirror, rows to reflect or clamp); interior strips skip all of that and address
 // memory incrementally.  NORM = accumulate the convergence sums of the (single) sweep.
@@ -656,10 +640,14 @@ static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStrea
     }
 #define HMI_CASE(M, KK) \
     if (method == M && k == KK) return launch_one<T, V, KK, M, false, TMA>(a, st, nblocks_out);
+#ifdef HMI_STREAM_LEAN      // experiment builds (tools/variants): the bench instantiations only
+    HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 6) HMI_CASE(HMI_CCST, 1) HMI_CASE(HMI_CCST, 3)
+#else
     HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 2) HMI_CASE(HMI_HARMONIC, 3)
     HMI_CASE(HMI_HARMONIC, 4) HMI_CASE(HMI_HARMONIC, 5) HMI_CASE(HMI_HARMONIC, 6)
     HMI_CASE(HMI_HARMONIC, 7) HMI_CASE(HMI_HARMONIC, 8)
     HMI_CASE(HMI_CCST, 1) HMI_CASE(HMI_CCST, 2) HMI_CASE(HMI_CCST, 3) HMI_CASE(HMI_CCST, 4)
+#endif
 #undef HMI_CASE
     return cudaErrorInvalidValue;
 }
@@ -667,17 +655,23 @@ static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStrea
 template <>
 cudaError_t launch_stream<float>(int method, int k, const StreamArgs<float> &a, cudaStream_t st, int *nblocks_out)
 {
+    if (a.tma == 3 && !a.do_norm && pipe_supports(method, k)) return launch_pipe<float>(method, k, a, st, nblocks_out);
+#ifndef HMI_STREAM_LEAN
     if (a.tma == 2) return launch_v<float, 4, 2>(method, k, a, st, nblocks_out);
     if (a.tma == 1) return launch_v<float, 4, 1>(method, k, a, st, nblocks_out);
+#endif
     return launch_v<float, 4, 0>(method, k, a, st, nblocks_out);
 }
 
 template <>
 cudaError_t launch_stream<double>(int method, int k, const StreamArgs<double> &a, cudaStream_t st, int *nblocks_out)
 {
+    if (a.tma == 3 && !a.do_norm && pipe_supports(method, k)) return launch_pipe<double>(method, k, a, st, nblocks_out);
     if (a.vec == 4) return launch_v<double, 4, 0>(method, k, a, st, nblocks_out);
+#ifndef HMI_STREAM_LEAN
     if (a.tma == 2) return launch_v<double, 2, 2>(method, k, a, st, nblocks_out);
     if (a.tma == 1) return launch_v<double, 2, 1>(method, k, a, st, nblocks_out);
+#endif
     return launch_v<double, 2, 0>(method, k, a, st, nblocks_out);
 }
 

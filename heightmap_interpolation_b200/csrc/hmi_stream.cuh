@@ -22,8 +22,8 @@ struct alignas(64) StreamArgs {
     int read_lo, read_hi;       // rows that exist in memory [read_lo, read_hi) (ghosts included)
     int top_border, bottom_border;
     int chunk_rows;             // rows per warp chunk; 0 = auto (wave-aware), < 0 = legacy auto rule
-    int vec;                    // cells per lane (fp64: 2 or 4; 0 = default)
-    int tma;                    // row staging: 0 = cp.async ring, 1 = 1-D bulk copies + mbarriers, 2 = 2-D tensor-map boxes
+    int vec;                    // cells per lane (fp64: 2 or 4, pipeline kernel 4 or 8; 0 = default)
+    int tma;                    // row staging: 0 = cp.async ring, 1 = 1-D bulk copies + mbarriers, 2 = 2-D tensor-map boxes, 3 = pipeline kernel
     int phys_row0;              // tma == 2: tensor-map row of slab row 0 (= ghost_top)
     int nwin, nchunks;          // filled by the launcher
     int n_edge, nchunks_e, chunk_rows_e;   // column-edge strips: how many (listed first), their chunking
@@ -37,6 +37,12 @@ struct alignas(64) StreamArgs {
 // k sweeps fused in one launch.  method in {HMI_HARMONIC, HMI_CCST}, 1 <= k <= stream_max_k().
 template <typename T>
 cudaError_t launch_stream(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out);
+
+// The same k fused sweeps on the warp-specialised pipeline kernel (hmi_pipe.cu; tma == 3): one loader warp and one
+// warp per sweep, rows handed on through shared-memory rings.  No convergence sums; k >= 2.
+template <typename T>
+cudaError_t launch_pipe(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out);
+bool pipe_supports(int method, int k);
 
 int stream_max_k(int method, int dtype);
 int stream_halo(int method, int k);                 // ghost rows/columns k fused sweeps consume

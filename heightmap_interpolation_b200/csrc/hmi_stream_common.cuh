@@ -30,6 +30,22 @@ __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, 
 template <typename T>
 __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
+// Sum of the four neighbours of centre row b (rows above/below + lane halos).  The association
+// (up + dn) + (l + r) is invariant under mirroring either axis (IEEE addition commutes), so a ghost
+// cell loaded from its mirror cell evolves *bit for bit* like that cell through the fused sweeps and
+// the result does not depend on how the sweeps were cut into launches or slabs.
+template <typename T, int V>
+__device__ __forceinline__ void sum4_row(const T (&up)[V], const T (&b)[V], const T (&dn)[V], T bl, T br,
+                                         T (&out)[V])
+{
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const T l = (v > 0) ? b[v - 1] : bl;
+        const T r = (v < V - 1) ? b[v + 1] : br;
+        out[v] = (up[v] + dn[v]) + (l + r);
+    }
+}
+
 template <int PH> struct Phase { static constexpr int value = PH; };
 
 __device__ __forceinline__ void lds16(unsigned addr, double (&v)[2])

@@ -183,7 +183,7 @@ def _problem(rows, cols, dtype, p=0.4, seed=3):
     return synthetic.zero_unknown(img, mask), mask
 
 
-@pytest.mark.parametrize("vec,tma", [(2, 0), (4, 0), (2, 1), (2, 2)])
+@pytest.mark.parametrize("vec,tma", [(2, 0), (4, 0), (2, 1), (2, 2), (4, 3), (8, 3)])
 @pytest.mark.parametrize("dt", ["f64", "f32"])
 @pytest.mark.parametrize("method,tb", [("harmonic", 1), ("harmonic", 2), ("harmonic", 3),
                                        ("harmonic", 4), ("harmonic", 5), ("harmonic", 8),
@@ -229,11 +229,15 @@ def test_row_staging_variants_are_bit_identical(method, tb, dt):
     the results must not differ in a single bit, on a grid large enough for many interior strips, and
     on a slab with ghost rows (tensor-map row 0 is then the first ghost row)."""
     img, mask = _problem(900, 1300, DTYPES[dt])
-    outs = [gpu_sweeps(method, "opencv", img, mask, 2 * tb + 1, kernel="stream", tb=tb, tma=tma)[0] for tma in (0, 1, 2)]
+    outs = [gpu_sweeps(method, "opencv", img, mask, 2 * tb + 1, kernel="stream", tb=tb, tma=tma)[0] for tma in (0, 1, 2, 3)]
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    # the warp-specialised pipeline kernel (tma = 3, hmi_pipe.cu) evaluates the same expressions in the same order
+    assert np.array_equal(outs[0], outs[3])
+    if dt == "f64":
+        assert np.array_equal(outs[0], gpu_sweeps(method, "opencv", img, mask, 2 * tb + 1, kernel="stream", tb=tb, tma=3, vec=8)[0])
     o = METHOD_OPTS[method]
     res = []
-    for tma in (0, 2):
+    for tma in (0, 2, 3):
         p = make_params(700, 1300, DTYPES[dt], METHODS[method], orientation=1, dt=o["update_step_size"],
                         tension=o.get("tension", 0.0), kernel=C.HMI_KERNEL_STREAM, temporal_block=tb,
                         ghost_top=100, ghost_bottom=100)
@@ -242,7 +246,7 @@ def test_row_staging_variants_are_bit_identical(method, tb, dt):
             s.set_problem_host(img, mask)
             s.sweeps(tb)
             res.append(s.get_result_host())
-    assert np.array_equal(res[0], res[1])
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
     ref = oracle_sweeps(method, "opencv", img, mask, tb)
     assert range_err(res[1], ref[100:800]) <= (1e-13 if dt == "f64" else 2e-6)
 
@@ -252,7 +256,7 @@ def test_stream_kernel_shapes_and_chunking(shape):
     img, mask = _problem(shape[0], shape[1], np.float64)
     ref = oracle_sweeps("ccst", "masked", img, mask, 6)
     for chunk in (0, 8, 50, 10 ** 6):
-        for vec, tma in ((2, 0), (4, 0), (2, 1), (2, 2)):
+        for vec, tma in ((2, 0), (4, 0), (2, 1), (2, 2), (4, 3), (8, 3)):
             got, info = gpu_sweeps("ccst", "masked", img, mask, 6, kernel="stream", tb=2,
                                    chunk_rows=chunk, vec=vec, tma=tma)
             assert range_err(got, ref) <= 1e-13, (shape, chunk, vec, tma)
