@@ -37,6 +37,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
+    if os.path.exists(LIB):          # a failed build must not leave the previous library behind
+        os.remove(LIB)
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]

@@ -284,6 +284,13 @@ static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaS
         a.top_border = p.ghost_top == 0; a.bottom_border = p.ghost_bottom == 0;
         a.chunk_rows = s->chunk_rows;
         a.vec = s->vec;
+        // fp64 harmonic on grids of many waves: 4 cells per lane (half the shuffles per cell, 112 of 128 columns
+        // of a strip useful instead of 52 of 64) beat 2 by 8-13 % at 16384^2 and 32768^2 and lose 6 % at 4096^2,
+        // where the launch is a single wave (profiles/r04_tune_peeled_steady_loop.log); CCST needs 234 registers
+        // with 4 cells and gains nothing.  Results are bit-identical either way.
+        if (s->vec == 0 && s->tma == 0 && p.dtype == HMI_F64 && p.method == HMI_HARMONIC && !do_norm && k >= 4 &&
+            (long long)(hi - lo) * p.cols >= (1LL << 26))
+            a.vec = 4;
         a.tma = s->tma;
         if (s->tma == 2) {
             const int rc = ensure_tmaps(s, hmi::stream_cells_per_lane(p.dtype, s->vec));

@@ -41,6 +41,9 @@
 #ifndef HMI_STREAM_MINB
 #define HMI_STREAM_MINB 1   // __launch_bounds__ min CTAs per SM (1 = let ptxas choose)
 #endif
+#ifndef HMI_STREAM_PEEL
+#define HMI_STREAM_PEEL 1   // 1 = interior strips run a steady-state row loop without fetch / store range tests
+#endif
 #ifndef HMI_STREAM_SKEW
 #define HMI_STREAM_SKEW 1   // 1 = stage s+1 consumes stage s's row one step later (independent stages)
 #endif
@@ -209,7 +212,9 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     int t2_box = 0;                                            // box being consumed
     unsigned t2_slot = 0, t2_par = 0;                          // ... its slot and mbarrier parity
 
-    auto issue = [&]() {
+    auto issue = [&](auto steady, auto in_loop) {
+        constexpr bool STEADY = decltype(steady)::value != 0;   // the caller guarantees ynext < yend
+        constexpr bool IN_LOOP = decltype(in_loop)::value != 0; // the caller sets wofs (the slot read one step ago)
         if (T2) return;
         if (TMA) {
             if (ynext < yend && lane == 0) {
@@ -233,7 +238,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             }
             widx = (widx + 1 == D) ? 0u : widx + 1;
         } else {
-            if (ynext < yend) {
+            if (STEADY || ynext < yend) {
                 const T *prow = gnext;
                 const uint8_t *mrow = mnext;
                 if (REDGE) {                       // reflect-101 at global edges, clamp to memory
@@ -254,20 +259,24 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             if (!REDGE) { gnext += a.pitch; mnext += a.mpitch; }
         }
         ++ynext;
-        wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
+        if (TMA || !IN_LOOP) wofs = (wofs + SLOT == D * SLOT) ? 0u : wofs + SLOT;
     };
 
     if (!T2) {
 #pragma unroll
-        for (int u = 0; u < D - 1; ++u) issue();
+        for (int u = 0; u < D - 1; ++u) issue(Phase<0>(), Phase<0>());
     }
 
     unsigned rofs = 0;                                         // ring byte offset of the slot to read
+    unsigned pofs = (D - 1) * SLOT;                            // ... of the slot read one step ago (refilled next)
     unsigned ridx = 0, rphase = 0;                             // TMA: slot index and mbarrier parity
     T *dptr = a.dst + (long long)(ybeg - LAG) * a.pitch + col0;   // row emitted by step ybeg
 
-    auto step = [&](auto ph, const int y) {
+    // STEADY steps (interior strips, cp.async staging): the row to fetch exists and the row emitted lies in
+    // [y0, y1), so neither is tested
+    auto step = [&](auto ph, auto steady, const int y) {
         constexpr int PH = decltype(ph)::value;
+        constexpr bool STEADY = decltype(steady)::value != 0;
         constexpr int IU = PH, IC = (PH + 1) % 3, IN = (PH + 2) % 3;
         if (T2) {
             if (PH == 0 && y < yend) mbar_wait(t2_bar + 8 * t2_slot, t2_par);   // the box rows y, y+1, y+2 sit in has landed
@@ -343,13 +352,14 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             }
         }
         mhist = (MH)(mhist << V) | (MH)mb;
+        if (!TMA) { wofs = pofs; pofs = rofs; }    // one wrapping counter serves reads and refills
         rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
         if (TMA) {
             ridx = (ridx + 1 == D) ? 0u : ridx + 1;
             if (ridx == 0) rphase ^= 1u;
             __syncwarp();                          // every lane is done with the slot about to be refilled
         }
-        issue();                                   // refills the slot read one step ago
+        issue(steady, Phase<1>());                 // refills the slot read one step ago
 
         T res[V];
         // Skewed: stages run last to first, each reads its window and then the stage before it
@@ -416,7 +426,7 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         }
         // res is sweep K of row y-LAG
         const int yo = y - LAG;
-        if (out_lane && yo >= y0 && yo < y1) {
+        if (out_lane && (STEADY || (yo >= y0 && yo < y1))) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 C16 t;
@@ -429,10 +439,27 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
         dptr += a.pitch;
     };
 
-    for (int y = ybeg; y < ystop; y += 3) {
-        step(Phase<0>(), y);
-        if (y + 1 < ystop) step(Phase<1>(), y + 1);
-        if (y + 2 < ystop) step(Phase<2>(), y + 2);
+    int y = ybeg;
+    // (not for four fused CCST sweeps: ptxas runs out of predicate registers on the second copy of that loop)
+    if (HMI_STREAM_PEEL && MODE == 0 && !TMA && !T2 && !NORM && !(CC && K >= 4)) {
+        // head: until the first emitted row reaches y0, in whole groups of three steps (the phases stay aligned)
+        const int y_store = ybeg + ((y0 + LAG - ybeg + 2) / 3) * 3;
+        const int y_fetch = yend - (D - 1);        // steps below this one still have a row to fetch
+        for (; y < y_store && y < ystop; y += 3) {
+            step(Phase<0>(), Phase<0>(), y);
+            if (y + 1 < ystop) step(Phase<1>(), Phase<0>(), y + 1);
+            if (y + 2 < ystop) step(Phase<2>(), Phase<0>(), y + 2);
+        }
+        for (; y + 2 < y_fetch; y += 3) {          // steady state (ystop > y_fetch always)
+            step(Phase<0>(), Phase<1>(), y);
+            step(Phase<1>(), Phase<1>(), y + 1);
+            step(Phase<2>(), Phase<1>(), y + 2);
+        }
+    }
+    for (; y < ystop; y += 3) {
+        step(Phase<0>(), Phase<0>(), y);
+        if (y + 1 < ystop) step(Phase<1>(), Phase<0>(), y + 1);
+        if (y + 2 < ystop) step(Phase<2>(), Phase<0>(), y + 2);
     }
     if (!TMA && !T2) cp_async_wait<0>();
     // T2: every box that was issued has been waited for (boxes start below yend and the loop runs to
@@ -640,7 +667,9 @@ static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStrea
     }
 #define HMI_CASE(M, KK) \
     if (method == M && k == KK) return launch_one<T, V, KK, M, false, TMA>(a, st, nblocks_out);
-#ifdef HMI_STREAM_LEAN      // experiment builds (tools/variants): the bench instantiations only
+#if defined(HMI_STREAM_ONLY_M)   // bisecting builds: one instantiation
+    HMI_CASE(HMI_STREAM_ONLY_M, HMI_STREAM_ONLY_K)
+#elif defined(HMI_STREAM_LEAN)      // experiment builds (tools/variants): the bench instantiations only
     HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 6) HMI_CASE(HMI_CCST, 1) HMI_CASE(HMI_CCST, 3)
 #else
     HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 2) HMI_CASE(HMI_HARMONIC, 3)
