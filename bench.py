@@ -432,6 +432,9 @@ def run_b200(args):
 
     if rank == 0:
         nlaunch = max(int(timing["launches"]), 1)
+        traffic = ncu_traffic("ccst_f64_k%d_%d" % (tb, GRID))       # one launch over the whole grid (N = 1 capture)
+        if traffic is not None and world > 1:
+            traffic = int(traffic / world)                        # a slab launch moves its share of it
         achieved = float(GRID) * GRID * S * steps / world / nlaunch * BYTES_PER_LUP[dkey] / (ms * 1e-3 / nlaunch) / 1e9
         out = {
             "metric": "grid-cell updates/s", "value": value, "unit": "GLUPS", "n_gpus": world,
@@ -450,7 +453,7 @@ def run_b200(args):
             "gpu_launches": int(timing["launches"]),
             "clocks": timing["clocks"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic("ccst_f64_k%d_%d" % (tb, GRID)),
+                         "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src,
                          "note": "per GPU: algorithmic 17 B per grid-cell update x %d sweeps fused per launch; temporal "
                                  "blocking lets achieved exceed the HBM peak" % tb},

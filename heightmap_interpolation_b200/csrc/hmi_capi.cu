@@ -256,7 +256,7 @@ static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaS
     int nblocks = 0;
     cudaError_t e;
     if (s->use_nl) {
-        if (k < 1 || k > hmi::stream_nl_max_k(p.method, p.dtype))
+        if (k < 1 || k > hmi::stream_nl_max_k(p.method, p.dtype, p.border))
             return fail(HMI_ERR_STATE, "the TV/AMLE kernel fuses at most two (fp32: three) sweeps");
         hmi::NLLaunch<T> l;
         memset(&l, 0, sizeof(l));
@@ -266,7 +266,7 @@ static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaS
         l.row_lo = lo; l.row_hi = hi;
         l.read_lo = -p.ghost_top; l.read_hi = p.rows + p.ghost_bottom;
         l.top_border = p.ghost_top == 0; l.bottom_border = p.ghost_bottom == 0;
-        l.method = p.method; l.sgn = p.orientation;
+        l.method = p.method; l.sgn = p.orientation; l.border = p.border;
         l.chunk_rows = s->chunk_rows;
         l.k = k;
         l.do_norm = do_norm ? 1 : 0;
@@ -284,6 +284,7 @@ static int run_block_t(hmi_solver *s, int k, int lo, int hi, bool do_norm, cudaS
         a.top_border = p.ghost_top == 0; a.bottom_border = p.ghost_bottom == 0;
         a.chunk_rows = s->chunk_rows;
         a.vec = s->vec;
+        a.border = p.border;
         // fp64 harmonic on grids of many waves: 4 cells per lane (half the shuffles per cell, 112 of 128 columns
         // of a strip useful instead of 52 of 64) beat 2 by 8-13 % at 16384^2 and 32768^2 and lose 6 % at 4096^2,
         // where the launch is a single wave (profiles/r04_tune_peeled_steady_loop.log); CCST needs 234 registers
@@ -600,13 +601,14 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     s->phys_rows = p.ghost_top + p.rows + p.ghost_bottom;
 
     // kernel selection
+    // (zero padding = the SciPy convolvers; the symmetric rule is only reachable through AMLE convolve_in_1d)
     const bool stream_ok = (p.method == HMI_HARMONIC || p.method == HMI_CCST) &&
-                           p.border == HMI_BORDER_REFLECT101;
+                           (p.border == HMI_BORDER_REFLECT101 || p.border == HMI_BORDER_ZERO);
     int tb = 1;
     bool use_stream = false;
     if (p.kernel == HMI_KERNEL_STREAM && !stream_ok && (p.method == HMI_HARMONIC || p.method == HMI_CCST)) {
         delete s;
-        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel needs reflect-101 borders");
+        return fail(HMI_ERR_UNSUPPORTED, "streaming kernel needs reflect-101 or zero-padded borders");
     }
     if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
         const int maxk = hmi::stream_max_k(p.method, p.dtype);
@@ -614,6 +616,8 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
         // at 4096^2), harmonic 6
         tb = p.temporal_block > 0 ? p.temporal_block : (p.method == HMI_CCST ? 3 : 6);
         if (tb > maxk) tb = maxk;
+        if (p.border == HMI_BORDER_ZERO)
+            while (tb > 1 && !hmi::stream_zero_supports(p.method, tb)) --tb;
         // the mirrored ghost loads need the mirror cell to exist: shrink the block on small grids
         const int min_dim = p.cols < p.rows ? p.cols : p.rows;
         while (tb > 1 && 2 * hmi::stream_halo(p.method, tb) + 2 > min_dim) --tb;
@@ -627,16 +631,15 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     s->use_stream = use_stream;
     s->tb = tb;
     // TV / AMLE: streaming kernel (reflect-101, grid not tiny)
-    const bool nl_ok = (p.method == HMI_TV || p.method == HMI_AMLE) && p.border == HMI_BORDER_REFLECT101 &&
-                       p.rows >= 8 && p.cols >= 8;
+    const bool nl_ok = hmi::stream_nl_supports(p.method, p.orientation, p.border) && p.rows >= 8 && p.cols >= 8;
     if (p.kernel == HMI_KERNEL_STREAM && (p.method == HMI_TV || p.method == HMI_AMLE) && !nl_ok) {
         delete s;
-        return fail(HMI_ERR_UNSUPPORTED, "streaming TV/AMLE kernel needs reflect-101 borders and a grid of at least 8x8");
+        return fail(HMI_ERR_UNSUPPORTED, "streaming TV/AMLE kernel: this orientation / border pair is served by the generic kernel (or the grid is under 8x8)");
     }
     s->use_nl = nl_ok && p.kernel != HMI_KERNEL_GENERIC;
     if (s->use_nl) {
         // two fused sweeps by default (profiles/r02_tune_tv_amle_k2.log); one on grids too small for the halo
-        const int maxk = hmi::stream_nl_max_k(p.method, p.dtype);
+        const int maxk = hmi::stream_nl_max_k(p.method, p.dtype, p.border);
         int k = p.temporal_block > 0 ? p.temporal_block : 2;
         if (k > maxk) k = maxk;
         if (p.rows < 16 || p.cols < 16) k = 1;
@@ -712,7 +715,7 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
     }
     if (!strcmp(key, "temporal_block")) {
         if (s->use_nl) {
-            const int maxk = hmi::stream_nl_max_k(s->p.method, s->p.dtype);
+            const int maxk = hmi::stream_nl_max_k(s->p.method, s->p.dtype, s->p.border);
             if (value < 1 || value > maxk || (value > 1 && (s->p.rows < 16 || s->p.cols < 16)))
                 return fail(HMI_ERR_BAD_ARG, "temporal_block out of range");
             s->tb = (int)value;
@@ -721,7 +724,8 @@ int hmi_set_option(hmi_solver *s, const char *key, int64_t value)
         if (!s->use_stream) return fail(HMI_ERR_UNSUPPORTED, "temporal_block applies to the streaming kernel");
         const int maxk = hmi::stream_max_k(s->p.method, s->p.dtype);
         const int min_dim = s->p.cols < s->p.rows ? s->p.cols : s->p.rows;
-        if (value < 1 || value > maxk || 2 * hmi::stream_halo(s->p.method, (int)value) + 2 > min_dim)
+        if (value < 1 || value > maxk || 2 * hmi::stream_halo(s->p.method, (int)value) + 2 > min_dim ||
+            (s->p.border == HMI_BORDER_ZERO && !hmi::stream_zero_supports(s->p.method, (int)value)))
             return fail(HMI_ERR_BAD_ARG, "temporal_block out of range");
         s->tb = (int)value;
         return HMI_OK;

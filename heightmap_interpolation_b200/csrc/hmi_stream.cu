@@ -96,7 +96,10 @@ template <> struct MaskHist<true> { typedef unsigned type; };
 // One warp streams its strip down one chunk of rows.  MODE 2 = the strip touches a grid edge (ghost
 // columns to mirror, rows to reflect or clamp); interior strips skip all of that and address
 // memory incrementally.  NORM = accumulate the convergence sums of the (single) sweep.
-template <typename T, int V, int K, int METHOD, int D, int MODE, bool NORM, int STG>
+// BRD = border rule: HMI_BORDER_REFLECT101, or HMI_BORDER_ZERO (the SciPy convolvers, convolver.py:17-18, 47-54):
+// every filtered array — f and, CCST, h = L f — reads zeros outside the grid.  Ghost cells of f then are
+// "known cells of value 0" (they stay 0 through all fused sweeps) and ghost cells of h are forced to 0.
+template <typename T, int V, int K, int METHOD, int D, int MODE, bool NORM, int STG, int BRD>
 __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsigned ring_s, const int lane,
                                             const int win, const int y0, const int y1, double &n_d2, double &n_f2,
                                             double &n_mx, double &n_nan)
@@ -112,6 +115,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
     constexpr int SK = G::SK, LAG = G::LAG;
     constexpr int RB = G::RB, NBX = G::NBX, FBOX = G::FBOX, MBOX = G::MBOX, MROW = G::MROW;
     static_assert(!T2 || MODE == 0, "tensor-map boxes serve interior strips only");
+    constexpr bool ZERO = (BRD == HMI_BORDER_ZERO) && MODE >= 1;
+    static_assert(BRD == HMI_BORDER_REFLECT101 || (BRD == HMI_BORDER_ZERO && STG == 0), "zero padding uses the cp.async staging");
     static_assert((LAG + 1) * V <= 64, "mask history does not fit 64 bits");
     static_assert(!NORM || K == 1, "the convergence sums are fused into single-sweep launches only");
 
@@ -243,7 +248,8 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                 const uint8_t *mrow = mnext;
                 if (REDGE) {                       // reflect-101 at global edges, clamp to memory
                     int ry = ynext;
-                    if (ry < 0 && a.top_border) ry = -ry;
+                    if (ZERO) ;                        // rows outside the grid are zeroed when they are consumed
+                    else if (ry < 0 && a.top_border) ry = -ry;
                     else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
                     ry = max(a.read_lo, min(a.read_hi - 1, ry));
                     prow = gbase + (long long)ry * a.pitch;
@@ -320,7 +326,19 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
             if (V == 4) mb = (w * 0x08040201u) >> 24;
             else mb = ((((w >> sh) & 0xffffu) * 0x0201u) >> 8) & 3u;
         }
-        if (CEDGE) {
+        if (ZERO) {
+            // zero padding: cells outside the grid hold 0 and count as known, so every fused sweep keeps them 0
+            const bool ghost_row = (y < 0 && a.top_border) || (y >= a.rows && a.bottom_border);
+            if (CEDGE) mb &= VMASK;
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const int c = col0 + q;
+                if (ghost_row || (CEDGE && (c < 0 || c >= a.cols))) {
+                    F[0][IN][q] = T(0);
+                    mb |= 1u << (V - 1 - q);
+                }
+            }
+        } else if (CEDGE) {
             // Ghost columns take the value and mask of their mirror cell, which sits in this
             // strip's ring slot (copied by another lane).  Lanes outside the allocation copied
             // nothing and read stale bytes, so clamp the bit group first.
@@ -390,6 +408,13 @@ __device__ __forceinline__ void stream_rows(const StreamArgs<T> &a, const unsign
                 // rin is row yy = y-2s of sweep s; hN = L f (row yy-1); output = sweep s+1 of row yy-2
 #pragma unroll
                 for (int v = 0; v < V; ++v) Hh[s][IN][v] = fma(T(-4), F[s][IC][v], s4[v]);
+                if (ZERO) {                        // h is zero-padded like f: its row here is y - s(R+SK) - 1
+                    const int hr = y - s * (R + SK) - 1;
+                    const bool ghost_row = (hr < 0 && a.top_border) || (hr >= a.rows && a.bottom_border);
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (ghost_row || (CEDGE && (col0 + v < 0 || col0 + v >= a.cols))) Hh[s][IN][v] = T(0);
+                }
                 sum4_row<T, V>(Hh[s][IU], Hh[s][IC], Hh[s][IN], HL[s], HR[s], s4);
                 HL[s] = shfl_up1(Hh[s][IN][V - 1]);
                 HR[s] = shfl_down1(Hh[s][IN][0]);
@@ -476,7 +501,7 @@ struct WarpRing {
                                           : (STG == 2 ? MaxOf<((CP + 127) / 128) * 128, G::RING_T2>::value : CP);
 };
 
-template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM, int STG>
+template <typename T, int V, int K, int METHOD, int D, int WPB, int MINB, bool NORM, int STG, int BRD>
 __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const __grid_constant__ StreamArgs<T> a)
 {
     typedef Geo<T, V, K, METHOD> G;
@@ -521,11 +546,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const __grid_con
         const bool row_edge = (ybeg < 0 && a.top_border) || (yend > a.rows && a.bottom_border) ||
                               (ybeg < a.read_lo) || (yend > a.read_hi);
         if (col_edge)
-            stream_rows<T, V, K, METHOD, D, 2, NORM, STG_EDGE>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 2, NORM, STG_EDGE, BRD>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else if (row_edge)
-            stream_rows<T, V, K, METHOD, D, 1, NORM, STG_EDGE>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 1, NORM, STG_EDGE, BRD>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows<T, V, K, METHOD, D, 0, NORM, STG>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows<T, V, K, METHOD, D, 0, NORM, STG, BRD>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -533,7 +558,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) stream_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 // host side
 
-template <typename T, int V, int K, int METHOD, bool NORM, int STG>
+template <typename T, int V, int K, int METHOD, bool NORM, int STG, int BRD = HMI_BORDER_REFLECT101>
 static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nblocks_out)
 {
     typedef Geo<T, V, K, METHOD> G;
@@ -542,7 +567,7 @@ static cudaError_t launch_one(const StreamArgs<T> &a0, cudaStream_t st, int *nbl
     StreamArgs<T> a = a0;
     a.nwin = (a.cols + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
-    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM, STG>;
+    auto kern = stream_kernel<T, V, K, METHOD, D, WPB, MINB, NORM, STG, BRD>;
     static int cta_slots = 0;         // per instantiation: CTAs resident on the whole GPU at once
     if (cta_slots == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -656,6 +681,31 @@ int stream_max_blocks(int method, int rows_total, int cols)
     return (int)((nwin * nch + 3) / 4 + 1);
 }
 
+// zero padding (the SciPy convolvers): default cells per lane, cp.async staging
+template <typename T, int V>
+static cudaError_t launch_zero(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
+{
+    constexpr int Z = HMI_BORDER_ZERO;
+    if (a.do_norm) {
+        if (k != 1) return cudaErrorInvalidValue;
+        if (method == HMI_HARMONIC) return launch_one<T, V, 1, HMI_HARMONIC, true, 0, Z>(a, st, nblocks_out);
+        if (method == HMI_CCST) return launch_one<T, V, 1, HMI_CCST, true, 0, Z>(a, st, nblocks_out);
+        return cudaErrorInvalidValue;
+    }
+#define HMI_CASE(M, KK) \
+    if (method == M && k == KK) return launch_one<T, V, KK, M, false, 0, Z>(a, st, nblocks_out);
+    HMI_CASE(HMI_HARMONIC, 1) HMI_CASE(HMI_HARMONIC, 2) HMI_CASE(HMI_HARMONIC, 3) HMI_CASE(HMI_HARMONIC, 4)
+    HMI_CASE(HMI_HARMONIC, 6)
+    HMI_CASE(HMI_CCST, 1) HMI_CASE(HMI_CCST, 2) HMI_CASE(HMI_CCST, 3)
+#undef HMI_CASE
+    return cudaErrorInvalidValue;
+}
+
+bool stream_zero_supports(int method, int k)
+{
+    return (method == HMI_HARMONIC && ((k >= 1 && k <= 4) || k == 6)) || (method == HMI_CCST && k >= 1 && k <= 3);
+}
+
 template <typename T, int V, int TMA>
 static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out)
 {
@@ -684,6 +734,7 @@ static cudaError_t launch_v(int method, int k, const StreamArgs<T> &a, cudaStrea
 template <>
 cudaError_t launch_stream<float>(int method, int k, const StreamArgs<float> &a, cudaStream_t st, int *nblocks_out)
 {
+    if (a.border == HMI_BORDER_ZERO) return launch_zero<float, 4>(method, k, a, st, nblocks_out);
     if (a.tma == 3 && !a.do_norm && pipe_supports(method, k)) return launch_pipe<float>(method, k, a, st, nblocks_out);
 #ifndef HMI_STREAM_LEAN
     if (a.tma == 2) return launch_v<float, 4, 2>(method, k, a, st, nblocks_out);
@@ -695,6 +746,7 @@ cudaError_t launch_stream<float>(int method, int k, const StreamArgs<float> &a, 
 template <>
 cudaError_t launch_stream<double>(int method, int k, const StreamArgs<double> &a, cudaStream_t st, int *nblocks_out)
 {
+    if (a.border == HMI_BORDER_ZERO) return launch_zero<double, 2>(method, k, a, st, nblocks_out);
     if (a.tma == 3 && !a.do_norm && pipe_supports(method, k)) return launch_pipe<double>(method, k, a, st, nblocks_out);
     if (a.vec == 4) return launch_v<double, 4, 0>(method, k, a, st, nblocks_out);
 #ifndef HMI_STREAM_LEAN

@@ -25,6 +25,7 @@ struct alignas(64) StreamArgs {
     int vec;                    // cells per lane (fp64: 2 or 4, pipeline kernel 4 or 8; 0 = default)
     int tma;                    // row staging: 0 = cp.async ring, 1 = 1-D bulk copies + mbarriers, 2 = 2-D tensor-map boxes, 3 = pipeline kernel
     int phys_row0;              // tma == 2: tensor-map row of slab row 0 (= ghost_top)
+    int border;                 // HMI_BORDER_REFLECT101 or HMI_BORDER_ZERO (zero: default vec, cp.async staging)
     int nwin, nchunks;          // filled by the launcher
     int n_edge, nchunks_e, chunk_rows_e;   // column-edge strips: how many (listed first), their chunking
     T dt, tension, one_minus_tension;
@@ -43,6 +44,7 @@ cudaError_t launch_stream(int method, int k, const StreamArgs<T> &a, cudaStream_
 template <typename T>
 cudaError_t launch_pipe(int method, int k, const StreamArgs<T> &a, cudaStream_t st, int *nblocks_out);
 bool pipe_supports(int method, int k);
+bool stream_zero_supports(int method, int k);       // fused-sweep depths instantiated for zero padding
 
 int stream_max_k(int method, int dtype);
 int stream_halo(int method, int k);                 // ghost rows/columns k fused sweeps consume

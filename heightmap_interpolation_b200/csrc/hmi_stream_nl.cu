@@ -81,7 +81,10 @@ __device__ __forceinline__ double select_known(unsigned known, double c, double 
 // emitted as its newest input row, so step y emits sweep K of row y - 2K and only that is stored.
 // One sweep consumes one column and one row of validity per side; the strip already carries a whole
 // lane (V cells) of halo per side, so K <= V costs no extra column overlap.
-template <typename T, int V, int METHOD, int SGN, int D, int MODE, bool NORM, int K>
+// BRD = border rule every filtered array (f of every sweep and the intermediates) carries: reflect-101
+// ("opencv", "masked*"), zero padding (the SciPy convolvers, convolver.py:17-18, 47-54) or SciPy's symmetric
+// 'reflect' (AMLE convolve_in_1d, amle_inpainter.py:26-37).  It only changes what a ghost cell holds.
+template <typename T, int V, int METHOD, int SGN, int D, int MODE, bool NORM, int K, int BRD>
 __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const unsigned ring_s, const int lane,
                                                const int win, const int y0, const int y1, double &n_d2,
                                                double &n_f2, double &n_mx, double &n_nan)
@@ -91,6 +94,7 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
     constexpr int N = G::N, NCH = G::NCH, HV = G::HV, S = G::S, ROW_BYTES = G::ROW_BYTES, SLOT = G::SLOT;
     constexpr bool TV = (METHOD == HMI_TV);
     constexpr bool REDGE = MODE >= 1, CEDGE = MODE == 2;
+    constexpr bool SYM = (BRD == HMI_BORDER_SYMMETRIC), ZERO = (BRD == HMI_BORDER_ZERO);
     constexpr unsigned VMASK = (1u << V) - 1u;
     constexpr int LAG = 2 * K;                         // step y emits sweep K of row y - 2K
     static_assert(K >= 1 && K <= 3 && K <= V, "temporal block deeper than the lane halo");
@@ -131,8 +135,9 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
             const uint8_t *mrow = mnext;
             if (REDGE) {                               // reflect-101 at the global edges, clamp to memory
                 int ry = ynext;
-                if (ry < 0 && a.top_border) ry = -ry;
-                else if (ry >= a.rows && a.bottom_border) ry = 2 * (a.rows - 1) - ry;
+                if (ZERO) ;                            // ghost rows are zeroed when they are consumed
+                else if (ry < 0 && a.top_border) ry = SYM ? -ry - 1 : -ry;
+                else if (ry >= a.rows && a.bottom_border) ry = SYM ? 2 * a.rows - 1 - ry : 2 * (a.rows - 1) - ry;
                 ry = max(a.read_lo, min(a.read_hi - 1, ry));
                 prow = gbase + (long long)arow(ry) * a.pitch;
                 mrow = mbase + (long long)arow(ry) * a.mpitch;
@@ -205,8 +210,11 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         const int c = col0 + v;
-                        if (c < a.clo || c >= a.chi) { // ghost column: value and mask of the mirror cell
-                            const int cm = (c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c;
+                        if (ZERO) {
+                            if (c < a.clo || c >= a.chi) F[0][IN][v] = T(0);
+                        } else if (c < a.clo || c >= a.chi) { // ghost column: value and mask of the mirror cell
+                            const int cm = SYM ? ((c < a.clo) ? 2 * a.clo - c - 1 : 2 * a.chi - 1 - c)
+                                               : ((c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c);
                             const int pos = max(0, min(32 * V - 1, cm - x0));
                             const int pl = pos / V, pv = pos % V;
                             const int pact = SGN > 0 ? pv : V - 1 - pv;    // actual element in lane pl
@@ -224,6 +232,12 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
                         }
                     }
                 }
+                if (ZERO && REDGE) {
+                    if (ys < rtop || ys >= rbot) {     // a row outside the grid
+#pragma unroll
+                        for (int v = 0; v < V; ++v) F[0][IN][v] = T(0);
+                    }
+                }
                 mhist = (mhist << V) | mb;
                 rofs = (rofs + SLOT == D * SLOT) ? 0u : rofs + SLOT;
                 issue();
@@ -234,18 +248,28 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
 #pragma unroll
                 for (int v = 0; v < V; ++v) F[s][IN][v] = res[v];
                 if (REDGE) {
-                    if (ys == rbot) {                  // first row below the grid := row rows-2 (slot IU)
+                    if (ZERO) {
+                        if (ys < rtop || ys >= rbot) { // rows outside the grid hold zeros
 #pragma unroll
-                        for (int v = 0; v < V; ++v) F[s][IN][v] = F[s][IU][v];
+                            for (int v = 0; v < V; ++v) F[s][IN][v] = T(0);
+                        }
+                    } else if (ys == rbot) {           // first row below the grid := row rows-2 (slot IU); symmetric: rows-1 (IC)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) F[s][IN][v] = SYM ? F[s][IC][v] : F[s][IU][v];
                     }
                 }
-                if (CEDGE) {                           // ghost columns := their mirror columns (other lanes)
+                if (CEDGE && ZERO) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (col0 + v < a.clo || col0 + v >= a.chi) F[s][IN][v] = T(0);
+                } else if (CEDGE) {                    // ghost columns := their mirror columns (other lanes)
                     T fix[V];
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         const int c = col0 + v;
                         const bool ghost = (c < a.clo || c >= a.chi);
-                        const int cm = (c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c;
+                        const int cm = SYM ? ((c < a.clo) ? 2 * a.clo - c - 1 : 2 * a.chi - 1 - c)
+                                           : ((c < a.clo) ? 2 * a.clo - c : 2 * (a.chi - 1) - c);
                         const int pos = max(0, min(32 * V - 1, cm - x0));
                         const int pl = pos / V, pv = pos % V;
                         T val = F[s][IN][v];
@@ -284,12 +308,15 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
             // them (ys-3) sits in slot IN
             const int r = ys - 2;
             if (REDGE) {
-                if (r == rtop) {                       // reflect-101 of the intermediate: [-1] := [1]
+                if (r == rtop) {                       // the intermediate above row 0: reflect-101 [-1] := [1], symmetric := [0], zero := 0
 #pragma unroll
-                    for (int v = 0; v < V; ++v) { P[s][IN][v] = P[s][IC][v]; Q[s][IN][v] = Q[s][IC][v]; }
-                    if (!TV && s > 0) {                // ... and of the field itself: f[-1] := f[1], so w0 = 0
+                    for (int v = 0; v < V; ++v) {
+                        P[s][IN][v] = ZERO ? T(0) : (SYM ? P[s][IU][v] : P[s][IC][v]);
+                        Q[s][IN][v] = ZERO ? T(0) : (SYM ? Q[s][IU][v] : Q[s][IC][v]);
+                    }
+                    if (!TV && s > 0 && !ZERO) {       // ... and the field itself: f[-1] := f[1], so w0 = 0 (symmetric: f[-1] := f[0])
 #pragma unroll
-                        for (int v = 0; v < V; ++v) v0[v] = T(0);
+                        for (int v = 0; v < V; ++v) v0[v] = SYM ? F[s][IC][v] - F[s][IU][v] : T(0);
                     }
                 }
             }
@@ -303,9 +330,13 @@ __device__ __forceinline__ void stream_rows_nl(const StreamNLArgs<T> &a, const u
             for (int v = 0; v < V; ++v) {
                 T pl = (v > 0) ? P[s][IU][v - 1] : Pl;
                 T ql = (v > 0) ? Q[s][IU][v - 1] : Ql;
-                if (CEDGE && col0 + v == a.clo) {      // reflect-101 of the intermediate: [-1] := [1]
-                    pl = (v < V - 1) ? P[s][IU][v + 1] : Pr;
-                    ql = (v < V - 1) ? Q[s][IU][v + 1] : Qr;
+                if (CEDGE && col0 + v == a.clo) {      // the intermediate left of column 0: reflect-101 [-1] := [1], symmetric := [0], zero := 0
+                    if (ZERO) { pl = T(0); ql = T(0); }
+                    else if (SYM) { pl = P[s][IU][v]; ql = Q[s][IU][v]; }
+                    else {
+                        pl = (v < V - 1) ? P[s][IU][v + 1] : Pr;
+                        ql = (v < V - 1) ? Q[s][IU][v + 1] : Qr;
+                    }
                 }
                 T stp;
                 if (TV) {
@@ -375,7 +406,7 @@ template <typename T, int METHOD, int K> struct NLBudget {
     static constexpr int MINB = K > 2 ? 2 : (K > 1 ? 3 : ((METHOD == HMI_TV) ? 5 : 4));
 };
 
-template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM, int K>
+template <typename T, int V, int METHOD, int SGN, int D, int WPB, bool NORM, int K, int BRD>
 __global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD, K>::MINB) stream_nl_kernel(const StreamNLArgs<T> a)
 {
     typedef GeoNL<T, V> G;
@@ -414,11 +445,11 @@ __global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD, K>::MINB) stream
         const bool row_edge = (y0 - K < 0 && a.top_border) || (y1 + K > a.rows && a.bottom_border) ||
                               (y0 - K < a.read_lo) || (y1 + K > a.read_hi) || (y0 <= 0 && a.top_border);
         if (col_edge)
-            stream_rows_nl<T, V, METHOD, SGN, D, 2, NORM, K>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 2, NORM, K, BRD>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else if (row_edge)
-            stream_rows_nl<T, V, METHOD, SGN, D, 1, NORM, K>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 1, NORM, K, BRD>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
         else
-            stream_rows_nl<T, V, METHOD, SGN, D, 0, NORM, K>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
+            stream_rows_nl<T, V, METHOD, SGN, D, 0, NORM, K, BRD>(a, ring_s, lane, win, y0, y1, n_d2, n_f2, n_mx, n_nan);
     }
     if (NORM) block_norm_reduce(n_d2, n_f2, n_mx, n_nan, sh, a.partials, a.counter, a.result);
 }
@@ -426,7 +457,7 @@ __global__ void __launch_bounds__(WPB * 32, NLBudget<T, METHOD, K>::MINB) stream
 // ------------------------------------------------------------------------------------------------
 // host side
 
-template <typename T, int V, int METHOD, int SGN, bool NORM, int K>
+template <typename T, int V, int METHOD, int SGN, bool NORM, int K, int BRD>
 static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nblocks_out)
 {
     typedef GeoNL<T, V> G;
@@ -453,7 +484,7 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     a.cbase = a.clo - (a.clo % V);
     a.nwin = (a.chi - a.cbase + G::S - 1) / G::S;
     const int nrows = a.row_hi - a.row_lo;
-    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM, K>;
+    auto kern = stream_nl_kernel<T, V, METHOD, SGN, D, WPB, NORM, K, BRD>;
     static int cta_slots = 0;
     if (cta_slots == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
@@ -487,9 +518,17 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
     return cudaGetLastError();
 }
 
-int stream_nl_max_k(int method, int dtype)
+int stream_nl_max_k(int method, int dtype, int border)
 {
-    return (method == HMI_TV && dtype == HMI_F32) ? 3 : 2;
+    return (method == HMI_TV && dtype == HMI_F32 && border == HMI_BORDER_REFLECT101) ? 3 : 2;
+}
+
+bool stream_nl_supports(int method, int sgn, int border)
+{
+    if (method != HMI_TV && method != HMI_AMLE) return false;
+    if (border == HMI_BORDER_REFLECT101) return true;
+    if (border == HMI_BORDER_ZERO) return sgn == -1;
+    return border == HMI_BORDER_SYMMETRIC && method == HMI_AMLE && sgn == -1;
 }
 
 int stream_nl_auto_chunk_rows(int nrows, int nwin)
@@ -506,10 +545,10 @@ int stream_nl_auto_chunk_rows(int nrows, int nwin)
 
 // three fused sweeps need three cells of lane halo: fp32 (V = 4) only; and TV only — ptxas cannot
 // allocate the predicates of the three-stage AMLE loop
-template <typename T, int V, int METHOD, int SGN>
+template <typename T, int V, int METHOD, int SGN, int BRD>
 static cudaError_t launch_nl_k3(const NLLaunch<T> &l, cudaStream_t st, int *nb)
 {
-    if constexpr (V >= 3 && METHOD == HMI_TV) return launch_nl_one<T, V, METHOD, SGN, false, 3>(l, st, nb);
+    if constexpr (V >= 3 && METHOD == HMI_TV && BRD == HMI_BORDER_REFLECT101) return launch_nl_one<T, V, METHOD, SGN, false, 3, BRD>(l, st, nb);
     else return cudaErrorInvalidValue;
 }
 
@@ -517,15 +556,19 @@ template <typename T, int V>
 static cudaError_t launch_nl_v(const NLLaunch<T> &l, cudaStream_t st, int *nb)
 {
     if (l.do_norm && l.k != 1) return cudaErrorInvalidValue;   // the norm is fused into single-sweep launches
-#define HMI_NL(M, SG)                                                                  \
-    if (l.method == M && l.sgn == SG) {                                                \
-        if (l.do_norm) return launch_nl_one<T, V, M, SG, true, 1>(l, st, nb);          \
-        if (l.k == 1) return launch_nl_one<T, V, M, SG, false, 1>(l, st, nb);          \
-        if (l.k == 2) return launch_nl_one<T, V, M, SG, false, 2>(l, st, nb);          \
-        if (l.k == 3) return launch_nl_k3<T, V, M, SG>(l, st, nb);                     \
+#define HMI_NL(M, SG, B)                                                               \
+    if (l.method == M && l.sgn == SG && l.border == B) {                               \
+        if (l.do_norm) return launch_nl_one<T, V, M, SG, true, 1, B>(l, st, nb);       \
+        if (l.k == 1) return launch_nl_one<T, V, M, SG, false, 1, B>(l, st, nb);       \
+        if (l.k == 2) return launch_nl_one<T, V, M, SG, false, 2, B>(l, st, nb);       \
+        if (l.k == 3) return launch_nl_k3<T, V, M, SG, B>(l, st, nb);                  \
         return cudaErrorInvalidValue;                                                  \
     }
-    HMI_NL(HMI_TV, 1) HMI_NL(HMI_TV, -1) HMI_NL(HMI_AMLE, 1) HMI_NL(HMI_AMLE, -1)
+    HMI_NL(HMI_TV, 1, HMI_BORDER_REFLECT101) HMI_NL(HMI_TV, -1, HMI_BORDER_REFLECT101)
+    HMI_NL(HMI_AMLE, 1, HMI_BORDER_REFLECT101) HMI_NL(HMI_AMLE, -1, HMI_BORDER_REFLECT101)
+    // the SciPy convolvers are convolutions (s = -1) with zero padding; AMLE convolve_in_1d is s = -1, symmetric
+    HMI_NL(HMI_TV, -1, HMI_BORDER_ZERO) HMI_NL(HMI_AMLE, -1, HMI_BORDER_ZERO)
+    HMI_NL(HMI_AMLE, -1, HMI_BORDER_SYMMETRIC)
 #undef HMI_NL
     return cudaErrorInvalidValue;
 }

@@ -18,6 +18,7 @@ struct NLLaunch {
     int top_border, bottom_border;
     int method;                  // HMI_TV or HMI_AMLE
     int sgn;                     // +1 correlation ("opencv"), -1 convolution ("masked*")
+    int border;                  // hmi_border (zero: sgn -1 only; symmetric: AMLE with sgn -1 only)
     int chunk_rows;              // 0 = auto (wave-aware), < 0 = legacy auto rule
     int k;                       // sweeps fused per launch (1..2, fp32 1..3; the norm needs 1)
     int do_norm;
@@ -49,6 +50,7 @@ template <typename T>
 cudaError_t launch_stream_nl(const NLLaunch<T> &l, cudaStream_t st, int *nblocks_out);
 
 int stream_nl_auto_chunk_rows(int nrows, int nwin);
-int stream_nl_max_k(int method, int dtype);   // 2; TV fp32 (four cells of lane halo): 3
+int stream_nl_max_k(int method, int dtype, int border = HMI_BORDER_REFLECT101);   // 2; TV fp32 reflect-101 (four cells of lane halo): 3
+bool stream_nl_supports(int method, int sgn, int border);
 
 }  // namespace hmi

@@ -251,6 +251,76 @@ def test_row_staging_variants_are_bit_identical(method, tb, dt):
     assert range_err(res[1], ref[100:800]) <= (1e-13 if dt == "f64" else 2e-6)
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("method,tb", [("harmonic", 1), ("harmonic", 3), ("harmonic", 6), ("ccst", 1), ("ccst", 2),
+                                       ("ccst", 3), ("tv", 1), ("tv", 2), ("amle", 1), ("amle", 2)])
+@pytest.mark.parametrize("shape", [(211, 333), (64, 61), (40, 1030), (515, 70)])
+def test_zero_padded_streaming_kernels_match_oracle(method, tb, dt, shape):
+    """The SciPy convolvers (convolver.py:17-18, 47-54: convolution orientation, zero padding of every filtered
+    array — f of every sweep and h / n / ux, uy) on the streaming kernels: ghost cells hold zeros at every fused
+    stage.  Unknown cells on every edge and corner, ragged strips and chunks, remainder blocks."""
+    img, mask = _problem(shape[0], shape[1], DTYPES[dt])
+    K = 2 * tb + 1
+    ref = oracle_sweeps(method, "scipy-signal", img, mask, K)
+    for chunk in (0, 29):
+        got, info = gpu_sweeps(method, "scipy-signal", img, mask, K, kernel="stream", tb=tb, chunk_rows=chunk)
+        assert info[0].startswith("stream") and info[1] == tb
+        assert np.array_equal(got[mask], img[mask])
+        err = range_err(got, ref)
+        assert err <= (1e-12 if dt == "f64" else 5e-6), (method, tb, dt, shape, chunk, err)
+    slow, _ = gpu_sweeps(method, "scipy-signal", img, mask, K, kernel="generic")
+    assert range_err(got, slow) <= (1e-12 if dt == "f64" else 5e-6)
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("tb", [1, 2])
+@pytest.mark.parametrize("shape", [(211, 333), (64, 61), (40, 1030), (515, 70)])
+def test_amle_1d_branch_on_the_streaming_kernel_matches_oracle(tb, dt, shape):
+    """AMLE convolve_in_1d (amle_inpainter.py:26-37: scipy.ndimage.convolve1d, SciPy's symmetric 'reflect'
+    border on f and on ux / uy, convolution orientation) on the streaming kernel."""
+    img, mask = _problem(shape[0], shape[1], DTYPES[dt])
+    K = 7
+    o = OracleInpainter("amle", convolver="opencv", max_iters=K, term_thres=1e-300, term_check_iters=10 ** 9,
+                        update_step_size=0.01, convolve_in_1d=True)
+    ref = o.inpaint_grid(img.copy(), mask)
+    for kernel, chunk in (("stream", 0), ("stream", 29), ("generic", 0)):
+        p = make_params(shape[0], shape[1], DTYPES[dt], C.HMI_AMLE, orientation=-1, border=C.HMI_BORDER_SYMMETRIC,
+                        dt=0.01, kernel=C.KERNELS[kernel], temporal_block=tb if kernel == "stream" else 0)
+        with Solver(p) as s:
+            if chunk:
+                s.set_option("chunk_rows", chunk)
+            s.set_problem_host(img, mask)
+            s.sweeps(K)
+            got = s.get_result_host()
+            assert s.kernel_name == ("stream_nl" if kernel == "stream" else "generic")
+        assert np.array_equal(got[mask], img[mask])
+        err = range_err(got, ref)
+        assert err <= (1e-12 if dt == "f64" else 5e-6), (kernel, chunk, tb, dt, shape, err)
+
+
+def test_zero_padded_streaming_kernels_on_slabs_and_with_the_fused_norm():
+    """Zero padding applies at the global top / bottom only: a slab with ghost rows must equal the rows of the
+    whole-grid solve; and the fused convergence sums of the zero-padded kernels equal the generic kernel's."""
+    img, mask = _problem(300, 450, np.float64)
+    for method, tb in (("ccst", 3), ("harmonic", 6), ("tv", 2), ("amle", 2)):
+        o = METHOD_OPTS[method]
+        whole, _ = gpu_sweeps(method, "scipy-signal", img, mask, tb, kernel="stream", tb=tb)
+        g = 2 * tb if method == "ccst" else tb
+        for a, b, gt, gb in ((0, 160, 0, g), (140, 300, g, 0), (100, 220, g, g)):
+            p = make_params(b - a, 450, np.float64, METHODS[method], orientation=-1, border=C.HMI_BORDER_ZERO,
+                            dt=o["update_step_size"], tension=o.get("tension", 0.0), epsilon=o.get("epsilon", 1e-2),
+                            kernel=C.HMI_KERNEL_STREAM, temporal_block=tb, ghost_top=gt, ghost_bottom=gb)
+            with Solver(p) as s:
+                s.set_problem_host(img[a - gt:b + gb], mask[a - gt:b + gb])
+                s.sweeps(tb)
+                assert np.array_equal(s.get_result_host(), whole[a:b]), (method, a, b)
+        fast, nf, _ = gpu_sweeps(method, "scipy-signal", img, mask, tb + 1, kernel="stream", tb=tb, want_norm=True)
+        slow, ns, _ = gpu_sweeps(method, "scipy-signal", img, mask, tb + 1, kernel="generic", want_norm=True)
+        assert range_err(fast, slow) <= 1e-12
+        assert nf.sum_d2 == pytest.approx(ns.sum_d2, rel=1e-9) and nf.sum_f2 == pytest.approx(ns.sum_f2, rel=1e-12)
+        assert nf.max_abs == pytest.approx(ns.max_abs, rel=1e-9)
+
+
 @pytest.mark.parametrize("shape", [(64, 64), (130, 120), (97, 1031), (1031, 97), (512, 512)])
 def test_stream_kernel_shapes_and_chunking(shape):
     img, mask = _problem(shape[0], shape[1], np.float64)
