@@ -612,9 +612,11 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
     }
     if (p.kernel != HMI_KERNEL_GENERIC && stream_ok) {
         const int maxk = hmi::stream_max_k(p.method, p.dtype);
-        // measured (profiles/r02_tune_*): CCST 3 in both precisions (fp32: 3 = 4 at 16384^2, 3 % ahead
-        // at 4096^2), harmonic 6
-        tb = p.temporal_block > 0 ? p.temporal_block : (p.method == HMI_CCST ? 3 : 6);
+        // measured: fp64 CCST 3, harmonic 6 (profiles/r02_tune_*); fp32 CCST 4, harmonic 8 since the
+        // steady-state row loop (profiles/r05_tune_f32_temporal_block.log: +4..16 % / +2..12 % over 3 / 6
+        // from 4096^2 to 32768^2)
+        const bool f32 = p.dtype == HMI_F32;
+        tb = p.temporal_block > 0 ? p.temporal_block : (p.method == HMI_CCST ? (f32 ? 4 : 3) : (f32 ? 8 : 6));
         if (tb > maxk) tb = maxk;
         if (p.border == HMI_BORDER_ZERO)
             while (tb > 1 && !hmi::stream_zero_supports(p.method, tb)) --tb;

@@ -139,7 +139,9 @@ int hmi_group_create(const hmi_params *params, const int32_t *devices, int32_t n
     int min_rows = params->rows;
     for (int i = 0; i < n; ++i) min_rows = (g->r1[i] - g->r0[i]) < min_rows ? (g->r1[i] - g->r0[i]) : min_rows;
     // a whole number of temporal blocks by default (harmonic 6, TV/AMLE 2, CCST 3 sweeps per launch)
-    int E = exchange_every > 0 ? exchange_every : (radius == 1 ? 18 : 12);
+    // a whole number of temporal blocks per exchange: CCST 3 / 4 sweeps per launch, harmonic 6 (fp32: 8), TV / AMLE 2
+    int E = exchange_every > 0 ? exchange_every
+                               : (radius == 1 ? (params->method == HMI_HARMONIC && params->dtype == HMI_F32 ? 16 : 18) : 12);
     if (n > 1 && E > (min_rows - 1) / radius) E = (min_rows - 1) / radius;
     if (E < 1) E = 1;
     g->exchange_every = E;

@@ -262,8 +262,9 @@ def inpaint_slab(inpainter, image, mask, rank=None, world=None, exchange_every=N
     bounds = slab_bounds(rows, world)
     r0, r1 = bounds[rank]
     min_rows = min(b - a for a, b in bounds)
-    if exchange_every is None:      # a whole number of temporal blocks (harmonic 6, TV/AMLE 2, CCST 3 sweeps per launch)
-        exchange_every = 18 if radius == 1 else 12
+    if exchange_every is None:      # a whole number of temporal blocks (harmonic 6 / fp32 8, TV/AMLE 2, CCST 3 / fp32 4 sweeps per launch)
+        harmonic_f32 = inpainter.METHOD == C.HMI_HARMONIC and image.dtype == np.float32
+        exchange_every = (16 if harmonic_f32 else 18) if radius == 1 else 12
     exchange_every = max(1, min(int(exchange_every), (min_rows - 1) // radius if world > 1 else 10 ** 9))
     ghost = radius * exchange_every if world > 1 else 0
     gt = ghost if rank > 0 else 0

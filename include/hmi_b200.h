@@ -227,7 +227,7 @@ int hmi_set_problem_host_blend(hmi_solver *fine, const void *image, size_t image
  * what `Inpainter(..., devices=[...]).inpaint(image, mask)` runs on, so that the reference's single call
  * site (apps/interpolate_netcdf4.py:200-204) can use the whole box.  `params` describes the whole grid
  * (ghost_* = 0; `device` is ignored); `exchange_every` = sweeps between halo exchanges (0 = default: 18
- * for the radius-1 methods, 12 for CCST), each slab carries radius * exchange_every ghost rows.  Small
+ * for the radius-1 methods — 16 for fp32 harmonic —, 12 for CCST), each slab carries radius * exchange_every ghost rows.  Small
  * grids use fewer devices than listed.  The functions mirror their single-solver namesakes. */
 typedef struct hmi_group hmi_group;
 int hmi_group_create(const hmi_params *params, const int32_t *devices, int32_t n_devices, int32_t exchange_every,

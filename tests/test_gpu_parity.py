@@ -566,6 +566,64 @@ def test_full_size_properties_16384_fp64_biharmonic():
         del fast, slab
 
 
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("method", ["harmonic", "ccst"])
+def test_symmetric_stencils_commute_with_mirrors_and_transposition_bit_for_bit(method, dt):
+    """A size-independent whole-grid property (no oracle needed): the harmonic and CCST stencils are symmetric
+    and the kernels associate the neighbour sum as (up + down) + (left + right), so solving the mirrored or the
+    transposed problem gives the mirrored / transposed result BIT FOR BIT — although every cell then sits in a
+    different strip, lane, chunk and code path (edge strips, ragged last strip, chunk seams)."""
+    rows, cols = 1217, 1531
+    mask = synthetic.mask_random((rows, cols), 0.4, seed=9)
+    img = synthetic.bathymetry((rows, cols), dtype=DTYPES[dt])
+    img[~mask] = 0
+    K = 11                                    # whole temporal blocks plus a remainder launch
+    want, info = gpu_sweeps(method, "opencv", img, mask, K)
+    assert info[0] == "stream"
+    for name, fwd in (("flipud", lambda a: a[::-1, :]), ("fliplr", lambda a: a[:, ::-1]),
+                      ("rot180", lambda a: a[::-1, ::-1]), ("transpose", lambda a: a.T)):
+        got, _ = gpu_sweeps(method, "opencv", np.ascontiguousarray(fwd(img)), np.ascontiguousarray(fwd(mask)), K)
+        assert np.array_equal(fwd(got) if name != "transpose" else got.T, want), (method, dt, name)
+
+
+def test_full_size_properties_32768_fp64_ccst_c5():
+    """BASELINE config 5, the bench workload (CCST tension 0.3, 32768^2 fp64, 40 % random mask seed 3), at
+    FULL size: known cells bit-exact over the whole grid; oracle parity on the four corners (global borders)
+    and on windows where 8-GPU slab seams would lie; and the whole-grid mirror property — the solve of the
+    grid rotated by 180 degrees equals the rotated solve bit for bit, all 2^30 cells, with every cell in a
+    different strip / chunk than before (32768 = 630 x 52 + 8 columns per strip)."""
+    psutil = pytest.importorskip("psutil")
+    if psutil.virtual_memory().available < 80 * 2 ** 30:
+        pytest.skip("needs ~40 GiB of host memory")
+    n, K = 32768, 9
+    img = np.empty((n, n), dtype=np.float64)
+    mask = np.empty((n, n), dtype=bool)
+    for r in range(0, n, 2048):
+        mask[r:r + 2048] = synthetic.mask_random((n, n), 0.40, seed=3, row_range=(r, r + 2048))
+        img[r:r + 2048] = synthetic.bathymetry((n, n), seed=7, row_range=(r, r + 2048))
+    img[~mask] = 0
+    fast, info = gpu_sweeps("ccst", "opencv", img, mask, K)
+    assert info[0] == "stream" and info[1] == 3 and info[2] == 3
+    for r in range(0, n, 2048):               # known cells, in row blocks (boolean indexing copies)
+        m = mask[r:r + 2048]
+        assert np.array_equal(fast[r:r + 2048][m], img[r:r + 2048][m]), r
+    c, h = 96, 2 * K + 2
+    windows = [(0, c, 0, c), (0, c, n - c, n), (n - c, n, 0, c), (n - c, n, n - c, n)]
+    windows += [(r - c // 2, r + c // 2, 12000, 12000 + c) for r in (4096, 16384, 28672)]
+    for r_lo, r_hi, c_lo, c_hi in windows:
+        a, b, cc, d = max(0, r_lo - h), min(n, r_hi + h), max(0, c_lo - h), min(n, c_hi + h)
+        ref = oracle_sweeps("ccst", "opencv", img[a:b, cc:d], mask[a:b, cc:d], K)
+        err = range_err(fast[r_lo:r_hi, c_lo:c_hi], ref[r_lo - a:r_hi - a, c_lo - cc:c_hi - cc])
+        assert err <= 1e-12, (r_lo, c_lo, err)
+    rot_img = np.ascontiguousarray(img[::-1, ::-1])
+    rot_mask = np.ascontiguousarray(mask[::-1, ::-1])
+    del img, mask
+    rot, _ = gpu_sweeps("ccst", "opencv", rot_img, rot_mask, K)
+    del rot_img, rot_mask
+    for r in range(0, n, 2048):
+        assert np.array_equal(rot[n - r - 2048:n - r][::-1, ::-1], fast[r:r + 2048]), r
+
+
 def test_full_size_properties_8192_fp32_tv():
     """BASELINE config 3 size (TV, 8192^2 fp32, large holes): known cells exact; a hole-containing
     window matches the oracle run on the window plus its dependency margin."""

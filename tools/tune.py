@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--mask", default="tracks")
     ap.add_argument("--vecs", default="2,4")
     ap.add_argument("--tma", type=int, default=0)
+    ap.add_argument("--border", default="reflect101", choices=["reflect101", "symmetric", "zero"])
+    ap.add_argument("--orientation", type=int, default=1)
     a = ap.parse_args()
     n = a.n
     for dt in a.dtypes.split(","):
@@ -63,7 +65,9 @@ def main():
                         continue
                     chunks = [int(c) for c in a.chunks.split(",")] if kernel == "stream" else [0]
                     for ch, sk in [(c, k) for c in chunks for k in ([int(x) for x in a.vecs.split(",")] if (kernel == "stream" and dt == "f64") else [0])]:
-                        p = make_params(n, n, dtype, code, orientation=1, dt=step, tension=0.3, epsilon=1.0,
+                        p = make_params(n, n, dtype, code, orientation=a.orientation, dt=step, tension=0.3, epsilon=1.0,
+                                        border={"reflect101": C.HMI_BORDER_REFLECT101, "symmetric": C.HMI_BORDER_SYMMETRIC,
+                                                "zero": C.HMI_BORDER_ZERO}[a.border],
                                         kernel=C.KERNELS[kernel], temporal_block=tb)
                         with Solver(p) as s:
                             if ch:
@@ -76,7 +80,7 @@ def main():
                             nsw = (nsw // tb) * tb
                             ms = time_sweeps(s, nsw)
                         g = n * n * nsw / (ms * 1e-3) / 1e9
-                        print("%-8s %s %-7s tb=%d chunk=%-4d vec=%d tma=%d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
+                        print(("" if a.border == "reflect101" else a.border + " border ") + "%-8s %s %-7s tb=%d chunk=%-4d vec=%d tma=%d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
                               % (method, dt, kernel, tb, ch, sk, a.tma, g, 100 * g * bpl / 6550.4, g * bpl), flush=True)
 
 
