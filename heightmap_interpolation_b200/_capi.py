@@ -129,6 +129,7 @@ SYMBOLS = {
                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "hmi_host_prefault": (ctypes.c_int, [_vp, _sz]),
     "hmi_release_cache": (ctypes.c_int, []),
+    "hmi_upload_pipeline_count": (ctypes.c_int64, []),
     "hmi_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64]),
     "hmi_set_term_thres": (ctypes.c_int, [_vp, ctypes.c_double]),
     "hmi_temporal_block": (ctypes.c_int, [_vp]),

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <mutex>
@@ -203,6 +204,16 @@ __global__ void fill_unknown_kernel(T *f, long long pitch, const uint8_t *m, lon
     if (j >= cols) return;
     for (int i = blockIdx.y; i < rows; i += gridDim.y)
         if (!m[(long long)i * mpitch + j]) f[(long long)i * pitch + j] = value;
+}
+
+// Pipelined upload (inpaint_host_impl): fold the convergence sums of one row band into the accumulator.
+__global__ void accumulate_norm_kernel(double *acc, const double *r, int first)
+{
+    if (first) { acc[0] = r[0]; acc[1] = r[1]; acc[2] = r[2]; acc[3] = r[3]; return; }
+    acc[0] += r[0];
+    acc[1] += r[1];
+    acc[2] = fmax(acc[2], r[2]);
+    acc[3] = fmax(acc[3], r[3]);
 }
 
 }  // namespace
@@ -663,7 +674,7 @@ int hmi_create(const hmi_params *params, hmi_solver **out)
         if ((e = cached_malloc(p.device, (void **)&s->mask, mask_bytes)) != cudaSuccess) break;
         {
             const size_t part = (size_t)s->max_blocks * 4 * sizeof(double);
-            s->scratch_bytes = (size_t)round_up((long long)(part + 64), 1 << 20);
+            s->scratch_bytes = (size_t)round_up((long long)(part + 128), 1 << 20);   // result, counter, error word, band accumulator
             if ((e = cached_malloc(p.device, &s->d_scratch, s->scratch_bytes)) != cudaSuccess) break;
             s->d_partials = (double *)s->d_scratch;
             s->d_result = (double *)((char *)s->d_scratch + part);
@@ -861,6 +872,241 @@ int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, 
 // fill: 0 = the grid is already initialised; 1 = unknown cells of the device copy <- fill_value;
 // 2 = as 1 and the caller's host array is initialised in place too (what the reference's Initializer
 // does first, initializer.py:15-18) — after the upload has read it, while the device solves.
+// ---- one-shot solve with the host <-> device copies overlapped with the solve -------------------
+//
+// hmi_inpaint_host* on a large grid is upload -> loop -> download, and the 18 GB a 32768^2 fp64 problem
+// moves over PCIe are 0.34 s of a 1.84 s call in which the SMs have nothing to do.  Both halves can be
+// hidden behind temporal blocks that run on row BANDS in a skewed order:
+//   * head start: the grid goes up in row bands, and as soon as band b has landed the bands above it
+//     advance — band b-1 does its first launch (iteration 0: one sweep with the convergence sums), band
+//     b-2 its second (a block of `tb` fused sweeps), band b-3 its third ...  A launch of a band reads
+//     radius*k halo rows of both neighbours at the previous time level, so a band may be one launch ahead
+//     of the band below it and no more; issuing each anti-diagonal (band + launch index = const) from
+//     its bottom band upwards on one stream satisfies every read-after-write and write-after-read
+//     dependence of the two ping-pong grids.  When the last band has landed the triangle is completed
+//     the other way round, so that every band has done the same nb launches = 1 + tb*(nb-1) sweeps, and
+//     the loop carries on with whole-grid launches;
+//   * drain: when a request of the loop is known to be the last one (it reaches max_iters — whatever its
+//     check says, the grid it leaves is the result), its last nb launches run in the same skewed order,
+//     so band 0 is final nb-1 diagonals before the last band, and every band is copied to the host as
+//     soon as it is final, while the bands below it are still being updated.  (A solve that stops on a
+//     passed check cannot do this: the result is only known once the check has been read.)
+// The kernels are indifferent to how sweeps are cut into launches, chunks or row ranges, so the result
+// is bit-identical to the plain path; convergence sums taken band-wise are the band sums folded in band
+// order (the plain path folds CTA partials in CTA order: the last bits of last_diff can differ).
+// If iteration 0 already meets the threshold (the reference returns after one update) the caller redoes
+// the solve on the plain path.
+static std::atomic<long long> g_pipelined_uploads{0};
+
+struct BandPlan {
+    int nb = 0;                 // row bands
+    std::vector<int> r0;        // band b = rows [r0[b], r0[b + 1])
+    long long extra = 0;        // head start: sweeps every band is ahead of iteration 0 when it is over
+};
+
+struct BandLaunch { int k; bool norm; };   // sweeps fused, with the convergence sums
+
+static bool plan_bands(const hmi_solver *s, BandPlan *pl)
+{
+    const hmi_params &p = s->p;
+    const char *env = getenv("HMI_UPLOAD_PIPELINE");      // 0 = off, 2 = also on small grids (tests)
+    const int mode = env ? atoi(env) : 1;
+    if (getenv("HMI_DEBUG"))
+        fprintf(stderr, "[hmi] plan_bands: mode %d stream %d nl %d tb %d radius %d rows %d T %lld maxit %lld\n", mode,
+                (int)s->use_stream, (int)s->use_nl, s->tb, s->radius, p.rows, (long long)p.term_check_iters, (long long)p.max_iters);
+    if (mode == 0 || p.ghost_top || p.ghost_bottom || !(s->use_stream || s->use_nl)) return false;
+    if (mode != 2 && ((long long)p.rows * p.cols < (1LL << 26) || p.rows < 4096)) return false;
+    const long long first_window = p.term_check_iters < p.max_iters - 1 ? p.term_check_iters : p.max_iters - 1;
+    // bands of 1024 rows, at most 32: on the 32768^2 bench workload 32 and 64 bands measure the same (end to end
+    // 87.6 / 87.3 % of the resident rate against 82 % without the overlap), 16 bands 85 % (profiles/r05_tune_pipeline_bands.log);
+    // a band launch is a partial wave and costs ~1.35x its share of a whole-grid launch, which eats part of the overlap
+    int nb = mode == 2 ? 8 : p.rows / 1024;
+    if (nb > 32) nb = 32;
+    if (const char *eb = getenv("HMI_PIPELINE_BANDS")) nb = atoi(eb) < nb ? atoi(eb) : nb;    // tuning
+    // the second request of the loop (T sweeps up to the next check, or max_iters - 1) must cover the head start,
+    // and a band must be taller than the halo a launch reads from it
+    while (nb >= 4 && ((long long)s->tb * (nb - 1) + 1 > first_window || p.rows / nb < 2 * s->radius * s->tb + 8)) nb /= 2;
+    if (nb < 4) return false;
+    if (getenv("HMI_DEBUG"))
+        fprintf(stderr, "[hmi] one-shot copies pipelined: %d bands of ~%d rows, head start %lld sweeps\n", nb, p.rows / nb,
+                (long long)s->tb * (nb - 1) + 1);
+    pl->nb = nb;
+    pl->extra = (long long)s->tb * (nb - 1);
+    pl->r0.resize(nb + 1);
+    for (int b = 0; b <= nb; ++b) pl->r0[b] = (int)((long long)p.rows * b / nb) & ~7;
+    pl->r0[nb] = p.rows;
+    return true;
+}
+
+// The launches of a skewed schedule: every band runs seq[0], seq[1], ... seq[M-1]; launch q reads grid
+// (base + q) & 1 and writes the other one.  issue(d) queues anti-diagonal d (band j runs launch d - j),
+// bottom band first.  Band sums of launches with `norm` are folded on the device in issue order.
+struct BandSchedule {
+    hmi_solver *s;
+    const BandPlan &pl;
+    std::vector<BandLaunch> seq;
+    int base;
+    cudaStream_t st;
+    double *acc;
+    bool acc_started = false;
+    int last_done = -1;          // bands 0 ... last_done have been issued their final launch
+
+    int issue(int d)
+    {
+        const int nb = pl.nb, M = (int)seq.size();
+        const int j_hi = d < nb - 1 ? d : nb - 1, j_lo = d - (M - 1) > 0 ? d - (M - 1) : 0;
+        for (int j = j_hi; j >= j_lo; --j) {
+            const int q = d - j;
+            s->cur = (base + q) & 1;
+            const int rc = run_block(s, seq[q].k, pl.r0[j], pl.r0[j + 1], seq[q].norm, st, false);
+            if (rc != HMI_OK) return rc;
+            if (seq[q].norm) {
+                accumulate_norm_kernel<<<1, 1, 0, st>>>(acc, s->d_result, acc_started ? 0 : 1);
+                acc_started = true;
+                if (cudaGetLastError() != cudaSuccess) return fail(HMI_ERR_CUDA, "norm accumulation launch failed");
+            }
+            if (q == M - 1) last_done = j;
+        }
+        return HMI_OK;
+    }
+    int diagonals() const { return pl.nb - 1 + (int)seq.size(); }
+    // after the last diagonal: the current grid, and the folded sums where the result of a check is read
+    int finish(bool with_norm)
+    {
+        s->cur = (base + (int)seq.size()) & 1;
+        s->last_main = st;
+        if (with_norm) CUDA_TRY(cudaMemcpyAsync(s->d_result, acc, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return HMI_OK;
+    }
+};
+
+// Upload in bands + head start.  On return every band has run iteration 0 and `extra` more sweeps, *nm holds
+// the convergence sums of iteration 0, and the caller's arrays have been read completely.
+static int upload_pipelined(hmi_solver *s, const BandPlan &pl, const void *image, const uint8_t *mask, int fill,
+                            double fill_value, hmi_norm *nm)
+{
+    const hmi_params &p = s->p;
+    const int nb = pl.nb;
+    CUDA_TRY(cudaSetDevice(p.device));
+    int rc = hmi::sync_solver(s);
+    if (rc != HMI_OK) return rc;
+    cudaStream_t st = s->own, cs = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const size_t wbytes = (size_t)p.cols * s->elem;
+    s->cur = 0;
+    s->has_problem = true;
+    s->halo_state = 0;
+    BandSchedule sch{s, pl, {}, 0, st, s->d_result + 8};
+    sch.seq.push_back({1, true});                                  // iteration 0
+    for (int q = 1; q < nb; ++q) sch.seq.push_back({s->tb, false});
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < nb && rc == HMI_OK; ++b) {
+        const int rows_b = pl.r0[b + 1] - pl.r0[b];
+        char *gdst = s->buf[0] + (size_t)pl.r0[b] * s->pitch * s->elem;
+        uint8_t *mdst = s->mask + (size_t)pl.r0[b] * s->mpitch;
+        // (synchronous on return: the band is in HBM before anything that reads it is queued)
+        if ((e = hmi::copy_h2d_2d(p.device, gdst, (size_t)s->pitch * s->elem, (const char *)image + (size_t)pl.r0[b] * wbytes,
+                                  wbytes, wbytes, rows_b, cs)) != cudaSuccess) break;
+        if ((e = hmi::copy_h2d_2d(p.device, mdst, (size_t)s->mpitch, mask + (size_t)pl.r0[b] * p.cols, (size_t)p.cols,
+                                  (size_t)p.cols, rows_b, cs)) != cudaSuccess) break;
+        normalize_mask_kernel<<<148, 256, 0, st>>>(mdst, (size_t)rows_b * s->mpitch);
+        if (fill) {
+            const dim3 grid((p.cols + 255) / 256, rows_b < 256 ? rows_b : 256);
+            if (p.dtype == HMI_F64)
+                fill_unknown_kernel<double><<<grid, 256, 0, st>>>((double *)gdst, s->pitch, mdst, s->mpitch, rows_b, p.cols, fill_value);
+            else
+                fill_unknown_kernel<float><<<grid, 256, 0, st>>>((float *)gdst, s->pitch, mdst, s->mpitch, rows_b, p.cols, (float)fill_value);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if (b >= 1) rc = sch.issue(b - 1);         // band b has landed: bands b-1 ... 0 advance by one launch
+    }
+    for (int d = nb - 1; d < sch.diagonals() && rc == HMI_OK && e == cudaSuccess; ++d) rc = sch.issue(d);
+    if (rc == HMI_OK && e == cudaSuccess) rc = sch.finish(true);
+    if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+    if (rc != HMI_OK) return rc;
+    if (e != cudaSuccess) return fail(HMI_ERR_CUDA, "pipelined upload failed: %s", cudaGetErrorString(e));
+    return fetch_norm(s, st, nm);
+}
+
+// The last request of the loop (n sweeps, the last one with the convergence sums if `norm`) with the download
+// overlapped: whole-grid launches first, then the last launches band-skewed, every band copied out once final.
+static int drain_pipelined(hmi_solver *s, const BandPlan &pl, long long n, bool norm, hmi_norm *nm, void *out)
+{
+    const hmi_params &p = s->p;
+    const int nb = pl.nb;
+    cudaStream_t st = s->own;
+    // the skewed tail: nb launches per band, the last of them the single sweep that carries the sums
+    std::vector<BandLaunch> seq;
+    long long tail = 0;
+    for (int q = 0; q < nb; ++q) {
+        const bool last = q == nb - 1;
+        seq.push_back({norm && last ? 1 : s->tb, norm && last});
+        tail += seq.back().k;
+    }
+    if (n < tail) {                                // short request: a shorter tail (at least the band of the sums)
+        seq.clear();
+        tail = 0;
+        long long left = norm ? n - 1 : n;         // (< tb * (nb - 1) with the sums, < tb * nb without)
+        while (left > 0) {
+            const int k = left < s->tb ? (int)left : s->tb;
+            seq.push_back({k, false});
+            left -= k;
+        }
+        if (norm) seq.push_back({1, true});
+        for (auto &l : seq) tail += l.k;
+        if (seq.empty()) return fail(HMI_ERR_STATE, "internal: empty drain");
+    }
+    int rc = do_sweeps(s, n - tail, false, st);
+    if (rc != HMI_OK) return rc;
+    BandSchedule sch{s, pl, seq, s->cur, st, s->d_result + 8};
+    const int final_cur = (s->cur + (int)seq.size()) & 1;
+    std::vector<cudaEvent_t> ev(nb, nullptr);
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < nb && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+    // The copies run on their own host thread: the launches below fill the driver's queue, so the thread that
+    // issues them only returns when most of them have already executed.
+    std::atomic<int> recorded{0};
+    std::atomic<bool> give_up{false};
+    cudaError_t e_dl = cudaSuccess;
+    const size_t wbytes = (size_t)p.cols * s->elem;
+    std::thread downloader;
+    if (e == cudaSuccess)
+        downloader = std::thread([&]() {
+            cudaStream_t cs = nullptr;
+            if ((e_dl = cudaSetDevice(p.device)) != cudaSuccess) return;
+            if ((e_dl = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking)) != cudaSuccess) return;
+            for (int b = 0; b < nb && e_dl == cudaSuccess; ++b) {
+                while (recorded.load(std::memory_order_acquire) <= b && !give_up.load()) std::this_thread::sleep_for(std::chrono::microseconds(20));
+                if (give_up.load()) break;
+                if ((e_dl = cudaEventSynchronize(ev[b])) != cudaSuccess) break;     // band b is final
+                const int rows_b = pl.r0[b + 1] - pl.r0[b];
+                const char *src = s->buf[final_cur] + (size_t)pl.r0[b] * s->pitch * s->elem;
+                e_dl = hmi::copy_d2h_2d(p.device, (char *)out + (size_t)pl.r0[b] * wbytes, wbytes, src, (size_t)s->pitch * s->elem,
+                                        wbytes, rows_b, cs);
+            }
+            cudaStreamSynchronize(cs);
+            cudaStreamDestroy(cs);
+        });
+    int n_rec = 0;
+    for (int d = 0; d < sch.diagonals() && rc == HMI_OK && e == cudaSuccess; ++d) {
+        rc = sch.issue(d);
+        for (; rc == HMI_OK && n_rec <= sch.last_done && e == cudaSuccess; ++n_rec) {
+            e = cudaEventRecord(ev[n_rec], st);
+            if (e == cudaSuccess) recorded.store(n_rec + 1, std::memory_order_release);
+        }
+    }
+    if (rc == HMI_OK && e == cudaSuccess) rc = sch.finish(norm);
+    if (rc != HMI_OK || e != cudaSuccess) give_up.store(true);
+    if (downloader.joinable()) downloader.join();
+    for (auto &x : ev) if (x) cudaEventDestroy(x);
+    if (rc != HMI_OK) return rc;
+    if (e != cudaSuccess || e_dl != cudaSuccess)
+        return fail(HMI_ERR_CUDA, "pipelined download failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e_dl));
+    if (norm) return fetch_norm(s, st, nm);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return HMI_OK;
+}
+
 static int inpaint_host_impl(const hmi_params *params, const void *image, const uint8_t *mask, int fill,
                              double fill_value, void *out, hmi_status *status)
 {
@@ -869,14 +1115,53 @@ static int inpaint_host_impl(const hmi_params *params, const void *image, const 
     int rc = hmi_create(params, &s);
     if (rc != HMI_OK) return rc;
     const size_t elem = params->dtype == HMI_F64 ? 8 : 4;
-    rc = hmi_set_problem_host(s, image, (size_t)params->cols * elem, mask, (size_t)params->cols);
     std::thread host_init;
-    if (rc == HMI_OK && fill == 2)
-        host_init = std::thread(hmi_host_fill_unknown, const_cast<void *>(image), mask,
-                                (int64_t)params->rows * params->cols, params->dtype, fill_value);
-    if (rc == HMI_OK && fill) rc = hmi::fill_unknown(s, fill_value);
-    if (rc == HMI_OK) rc = hmi_run(s, s->own, status);
-    if (rc == HMI_OK) rc = hmi_get_result_host(s, out, (size_t)params->cols * elem);
+    auto start_host_init = [&]() {                 // the caller's array has been read: initialise it in place
+        if (fill == 2 && !host_init.joinable())
+            host_init = std::thread(hmi_host_fill_unknown, const_cast<void *>(image), mask,
+                                    (int64_t)params->rows * params->cols, params->dtype, fill_value);
+    };
+    BandPlan pl;
+    bool plain = !plan_bands(s, &pl);
+    bool downloaded = false;
+    if (!plain) {
+        bool first = true;
+        long long ahead = 0, done = 0;
+        rc = hmi::reference_loop(s->p, [&](long long n, bool norm, hmi_norm *nm) {
+            int r;
+            if (first) {                           // iteration 0 (n == 1, with the sums) + the head start
+                first = false;
+                r = upload_pipelined(s, pl, image, mask, fill, fill_value, nm);
+                if (r == HMI_OK) g_pipelined_uploads.fetch_add(1);
+                start_host_init();
+                ahead = pl.extra;
+                done = 1;
+                return r;
+            }
+            const long long m = n - ahead;         // >= 1 by plan_bands
+            ahead = 0;
+            done += n;
+            if (done == s->p.max_iters) {          // the last request, whatever its check says: overlap the download
+                r = drain_pipelined(s, pl, m, norm, nm, out);
+                downloaded = r == HMI_OK;
+                return r;
+            }
+            r = do_sweeps(s, m, norm, s->own);
+            if (r == HMI_OK && norm) r = fetch_norm(s, s->own, nm);
+            return r;
+        }, status);
+        if (rc == HMI_OK) rc = cudaStreamSynchronize(s->own) == cudaSuccess ? HMI_OK : fail(HMI_ERR_CUDA, "solve failed");
+        // converged at iteration 0: the reference returns the grid after ONE update, the bands are further on
+        if (rc == HMI_OK && status->converged && status->updates_done == 1) plain = true;
+        if (plain && host_init.joinable()) host_init.join();
+    }
+    if (plain && rc == HMI_OK) {
+        rc = hmi_set_problem_host(s, image, (size_t)params->cols * elem, mask, (size_t)params->cols);
+        if (rc == HMI_OK) start_host_init();
+        if (rc == HMI_OK && fill) rc = hmi::fill_unknown(s, fill_value);
+        if (rc == HMI_OK) rc = hmi_run(s, s->own, status);
+    }
+    if (rc == HMI_OK && !downloaded) rc = hmi_get_result_host(s, out, (size_t)params->cols * elem);
     if (host_init.joinable()) host_init.join();
     hmi_destroy(s);
     return rc;
@@ -1060,6 +1345,8 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes)
     *pitch_bytes = (size_t)s->mpitch;
     return HMI_OK;
 }
+
+int64_t hmi_upload_pipeline_count(void) { return (int64_t)g_pipelined_uploads.load(); }
 
 int hmi_release_cache(void)
 {

@@ -187,6 +187,13 @@ int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, 
 int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t *mask, void *out,
                      hmi_status *status);
 
+/* On large grids (>= 2^26 cells, >= 4096 rows, streaming kernels) the one-shot calls upload the grid in row
+ * bands and overlap the upload with the first temporal blocks of the bands that have already landed
+ * (csrc/hmi_capi.cu: upload_pipelined); the result is bit-identical to upload-then-solve.  Environment
+ * variable HMI_UPLOAD_PIPELINE=0 turns it off (=2 forces it on small grids, for tests).  The counter says
+ * how many one-shot solves of this process took the pipelined route (tests, bench). */
+int64_t hmi_upload_pipeline_count(void);
+
 /* hmi_inpaint_host with the 'zeros' / 'mean' initialiser fused in: after the upload the unknown cells
  * (mask == 0) of the device copy are set to `fill_value`, so the caller can initialise its own host
  * array (the reference does that in place, inpainting/initializer.py:15-18) concurrently with the
