@@ -884,12 +884,15 @@ int hmi_get_result_device(hmi_solver *s, void *out_dev, size_t out_pitch_bytes, 
 //     of the band below it and no more; issuing each anti-diagonal (band + launch index = const) from
 //     its bottom band upwards on one stream satisfies every read-after-write and write-after-read
 //     dependence of the two ping-pong grids.  When the last band has landed the triangle is completed
-//     the other way round, so that every band has done the same nb launches = 1 + tb*(nb-1) sweeps, and
-//     the loop carries on with whole-grid launches;
+//     the other way round — the bands nb-1-q ... nb-1 are then all at time level q, so launch q runs on
+//     them as ONE whole-wave launch — until every band has done the same nb launches = 1 + tb*(nb-1)
+//     sweeps, and the loop carries on with whole-grid launches;
 //   * drain: when a request of the loop is known to be the last one (it reaches max_iters — whatever its
-//     check says, the grid it leaves is the result), its last nb launches run in the same skewed order,
-//     so band 0 is final nb-1 diagonals before the last band, and every band is copied to the host as
-//     soon as it is final, while the bands below it are still being updated.  (A solve that stops on a
+//     check says, the grid it leaves is the result), its last nb launches run skewed the same way:
+//     first the ramp that lets band 0 run ahead (launch q on the bands 0 ... nb-1-q, one whole-wave
+//     launch each), then band by band along the anti-diagonals, so band 0 is final nb-1 diagonals before
+//     the last band, and every band is copied to the host as soon as it is final, while the bands below
+//     it are still being updated.  (A solve that stops on a
 //     passed check cannot do this: the result is only known once the check has been read.)
 // The kernels are indifferent to how sweeps are cut into launches, chunks or row ranges, so the result
 // is bit-identical to the plain path; convergence sums taken band-wise are the band sums folded in band
@@ -969,6 +972,20 @@ struct BandSchedule {
         }
         return HMI_OK;
     }
+    // launch q on the contiguous bands [j_lo, j_hi], which are all at time level q, as ONE launch (full waves)
+    int issue_range(int q, int j_lo, int j_hi)
+    {
+        s->cur = (base + q) & 1;
+        const int rc = run_block(s, seq[q].k, pl.r0[j_lo], pl.r0[j_hi + 1], seq[q].norm, st, false);
+        if (rc != HMI_OK) return rc;
+        if (seq[q].norm) {
+            accumulate_norm_kernel<<<1, 1, 0, st>>>(acc, s->d_result, acc_started ? 0 : 1);
+            acc_started = true;
+            if (cudaGetLastError() != cudaSuccess) return fail(HMI_ERR_CUDA, "norm accumulation launch failed");
+        }
+        if (q == (int)seq.size() - 1 && j_hi > last_done) last_done = j_hi;
+        return HMI_OK;
+    }
     int diagonals() const { return pl.nb - 1 + (int)seq.size(); }
     // after the last diagonal: the current grid, and the folded sums where the result of a check is read
     int finish(bool with_norm)
@@ -1020,7 +1037,9 @@ static int upload_pipelined(hmi_solver *s, const BandPlan &pl, const void *image
         if ((e = cudaGetLastError()) != cudaSuccess) break;
         if (b >= 1) rc = sch.issue(b - 1);         // band b has landed: bands b-1 ... 0 advance by one launch
     }
-    for (int d = nb - 1; d < sch.diagonals() && rc == HMI_OK && e == cudaSuccess; ++d) rc = sch.issue(d);
+    // everything is in HBM: the bands catch up with band 0.  Bands nb-1-q ... nb-1 are all at time level q now,
+    // so launch q runs on them as one whole-wave launch (band launches are partial waves and cost ~1.35x)
+    for (int q = 0; q < nb && rc == HMI_OK && e == cudaSuccess; ++q) rc = sch.issue_range(q, nb - 1 - q, nb - 1);
     if (rc == HMI_OK && e == cudaSuccess) rc = sch.finish(true);
     if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
     if (rc != HMI_OK) return rc;
@@ -1088,12 +1107,23 @@ static int drain_pipelined(hmi_solver *s, const BandPlan &pl, long long n, bool 
             cudaStreamDestroy(cs);
         });
     int n_rec = 0;
-    for (int d = 0; d < sch.diagonals() && rc == HMI_OK && e == cudaSuccess; ++d) {
-        rc = sch.issue(d);
+    auto publish = [&]() {                         // bands 0 ... last_done are final: tell the downloader
         for (; rc == HMI_OK && n_rec <= sch.last_done && e == cudaSuccess; ++n_rec) {
             e = cudaEventRecord(ev[n_rec], st);
             if (e == cudaSuccess) recorded.store(n_rec + 1, std::memory_order_release);
         }
+    };
+    // ramp: band 0 runs ahead.  Launch q covers the bands 0 ... M-1-q, all at time level q: one whole-wave launch
+    const int M = (int)seq.size();
+    for (int q = 0; q < M && rc == HMI_OK && e == cudaSuccess; ++q) {
+        const int j_hi = M - 1 - q < nb - 1 ? M - 1 - q : nb - 1;
+        rc = sch.issue_range(q, 0, j_hi);
+    }
+    publish();                                     // band 0 is final
+    // the bands below finish one anti-diagonal after the other while the copies run
+    for (int d = M; d < sch.diagonals() && rc == HMI_OK && e == cudaSuccess; ++d) {
+        rc = sch.issue(d);
+        publish();
     }
     if (rc == HMI_OK && e == cudaSuccess) rc = sch.finish(norm);
     if (rc != HMI_OK || e != cudaSuccess) give_up.store(true);

@@ -64,6 +64,8 @@ def main():
         dtype = np.float64 if dt == "f64" else np.float32
         for method in a.methods.split(","):
             cls, mopts, radius, E = CASES[method]
+            if method == "harmonic" and dt == "f32":
+                E = 16                      # two blocks of the eight sweeps fp32 harmonic fuses per launch (library default)
             if method == "ccst":
                 mopts = dict(mopts, tension=a.tension)
             for kv in filter(None, a.exchange.split(",")):
