@@ -920,11 +920,13 @@ static bool plan_bands(const hmi_solver *s, BandPlan *pl)
     if (mode == 0 || p.ghost_top || p.ghost_bottom || !(s->use_stream || s->use_nl)) return false;
     if (mode != 2 && ((long long)p.rows * p.cols < (1LL << 26) || p.rows < 4096)) return false;
     const long long first_window = p.term_check_iters < p.max_iters - 1 ? p.term_check_iters : p.max_iters - 1;
-    // bands of 1024 rows, at most 32: on the 32768^2 bench workload 32 and 64 bands measure the same (end to end
-    // 87.6 / 87.3 % of the resident rate against 82 % without the overlap), 16 bands 85 % (profiles/r05_tune_pipeline_bands.log);
-    // a band launch is a partial wave and costs ~1.35x its share of a whole-grid launch, which eats part of the overlap
-    int nb = mode == 2 ? 8 : p.rows / 1024;
-    if (nb > 32) nb = 32;
+    // bands of 512 rows, at most 64.  The band-by-band launches are partial waves (~1.35x their share of a whole-grid
+    // launch), but they run under the copies; what they hide is the triangle nb/2 launches deep, which should
+    // match the copy time (32768^2 fp64: 175 ms up / 156 ms down against 4.5 ms per launch).  Measured on the bench
+    // workload, end to end as a share of the resident rate: no overlap 82.0 %, 32 bands 88.4 %, 64 bands 90.3 %
+    // (profiles/r05_tune_pipeline_bands_merged_ramps.log; before the ramps ran as whole-wave launches 87.6 / 87.3 %)
+    int nb = mode == 2 ? 8 : p.rows / 512;
+    if (nb > 64) nb = 64;
     if (const char *eb = getenv("HMI_PIPELINE_BANDS")) nb = atoi(eb) < nb ? atoi(eb) : nb;    // tuning
     // the second request of the loop (T sweeps up to the next check, or max_iters - 1) must cover the head start,
     // and a band must be taller than the halo a launch reads from it

@@ -78,7 +78,7 @@ def test_pipelined_upload_masked_orientation_and_converged_at_iteration_zero(mon
 def test_pipelined_upload_is_the_default_on_large_grids_and_not_on_small_ones(monkeypatch):
     monkeypatch.delenv("HMI_UPLOAD_PIPELINE", raising=False)
     lib = C.lib()
-    n = 8192                                                  # 2^26 cells, 8 bands of 1024 rows
+    n = 8192                                                  # 2^26 cells, 16 bands of 512 rows
     mask = synthetic.mask_random(n, 0.4, seed=3)
     img = synthetic.bathymetry(n, dtype=np.float32)
     img[~mask] = 0
