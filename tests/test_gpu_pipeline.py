@@ -75,6 +75,25 @@ def test_pipelined_upload_masked_orientation_and_converged_at_iteration_zero(mon
     assert np.array_equal(got, want)
 
 
+def test_pipelined_copies_through_inpaint_grid_and_a_preallocated_result(monkeypatch):
+    """inpaint_grid() on an already initialised array (hmi_inpaint_host: no fused initialiser) into out=."""
+    rows, cols = 1100, 1300
+    mask = synthetic.mask_random((rows, cols), 0.35, seed=4)
+    img = synthetic.bathymetry((rows, cols), dtype=np.float32)
+    img[~mask] = -2500.0
+    opts = dict(METHOD_OPTS["amle"], convolver="opencv", term_check_iters=40, max_iters=130, term_thres=1e-300)
+    res = {}
+    for mode in (0, 2):
+        monkeypatch.setenv("HMI_UPLOAD_PIPELINE", str(mode))
+        before = C.lib().hmi_upload_pipeline_count()
+        out = np.full((rows, cols), np.nan, dtype=np.float32)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = hmi.AMLEInpainter(**opts).inpaint_grid(img, mask, out=out)
+        assert got is out and C.lib().hmi_upload_pipeline_count() - before == (1 if mode else 0)
+        res[mode] = out
+    assert np.array_equal(res[2], res[0]) and not np.isnan(res[2]).any()
+
+
 def test_pipelined_upload_is_the_default_on_large_grids_and_not_on_small_ones(monkeypatch):
     monkeypatch.delenv("HMI_UPLOAD_PIPELINE", raising=False)
     lib = C.lib()
