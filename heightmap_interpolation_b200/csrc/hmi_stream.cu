@@ -610,7 +610,7 @@ int stream_cta_slots(const void *kernel, int threads, size_t smem)
 }
 
 void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, double edge_cost,
-                        int *chunk_rows, int *chunk_rows_edge)
+                        int *chunk_rows, int *chunk_rows_edge, int fill)
 {
     // Wave-aware chunk heights.  Every warp streams (chunk + 2*halo) rows plus a pipeline fill and
     // the launch takes ceil(CTAs / resident CTAs) rounds of that; a fixed chunk height leaves the
@@ -621,9 +621,21 @@ void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int 
     // shorter and are scheduled first; without that a single full wave is slower than three ragged
     // ones, because the whole launch waits for the two edge strips (profiles/r02_tune_skew_ab.log,
     // profiles/r02_tune_tv_chunks.log).
-    const int fill = 8;
+    // fill = a chunk's fixed cost in rows (pipeline fill, ring prefetch, prologue)
+    // Load balance.  A launch of r rounds does not take r times one round: all warps of a round start together, the
+    // round ends with its slowest warp (edge strips, DRAM page conflicts) and the SMs idle while it drains, so a
+    // launch of few long rounds loses to one of a few more, shorter ones although those recompute more overlap rows.
+    // Forcing the number of rounds (profiles/r05_tune_picker_min_rounds.log): a 4096 x 32768 fp32 slab, harmonic K = 8,
+    // 2 / 3 / 4 / 6 / 8 rounds 2207 / 2400 / 2434 / 2306 / 2175 GLUPS; a 512-row band of the pipelined copies, CCST fp64,
+    // 2 / 3 / 4 / 6 rounds 480 / 551 / 548 / 490; 4096^2 CCST fp64 1 / 2 / 3 rounds 597 / 612 / 569.  Half a round of
+    // drain time per launch reproduces every one of those optima (and leaves many-wave launches alone).
+    static double round_bias = -1.0;
+    if (round_bias < 0.0) round_bias = getenv("HMI_PICK_ROUND_BIAS") ? atof(getenv("HMI_PICK_ROUND_BIAS")) : 0.5;
+    // (chunks under ~48 rows never pay: with the load-balance term the model would cut a 4096^2 fp32 TV grid into three
+    // rounds of 32-row chunks, measured 4 % slower than one round of 100-row chunks — a chunk's fixed cost is more than
+    // the 2*halo + fill rows counted here, profiles/r05_tune_picker_round_bias_nl_f32.log)
     int lo = 4 * halo;
-    if (lo < 24) lo = 24;
+    if (lo < 48) lo = 48;
     if (lo > nrows) lo = nrows;
     double best = 1e300;
     int best_ch = nrows, best_che = nrows;
@@ -639,7 +651,7 @@ void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int 
         const long long warps = (long long)n_edge * ne + (long long)(nwin - n_edge) * n;
         const long long ctas = (warps + wpb - 1) / wpb;
         const long long rounds = (ctas + cta_slots - 1) / cta_slots;
-        const double cost = (double)rounds * (ch + 2 * halo + fill) * (1.0 + ch / 8192.0);
+        const double cost = ((double)rounds + round_bias) * (ch + 2 * halo + fill) * (1.0 + ch / 8192.0);
         if (cost <= best) { best = cost; best_ch = ch; best_che = che; }
     }
     *chunk_rows = best_ch < 8 ? 8 : best_ch;

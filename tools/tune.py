@@ -44,14 +44,16 @@ def main():
     ap.add_argument("--mask", default="tracks")
     ap.add_argument("--vecs", default="2,4")
     ap.add_argument("--tma", type=int, default=0)
+    ap.add_argument("--rows", type=int, default=0, help="rows of the grid if not square (a row slab: --rows 4096 --n 32768)")
     ap.add_argument("--border", default="reflect101", choices=["reflect101", "symmetric", "zero"])
     ap.add_argument("--orientation", type=int, default=1)
     a = ap.parse_args()
     n = a.n
+    rows = a.rows or n
     for dt in a.dtypes.split(","):
         dtype = np.float64 if dt == "f64" else np.float32
-        img = synthetic.bathymetry(n, dtype=dtype)
-        mask = synthetic.mask_tracks(n) if a.mask == "tracks" else synthetic.mask_random(n, 0.4, 3)
+        img = synthetic.bathymetry((rows, n), dtype=dtype)
+        mask = synthetic.mask_tracks((rows, n)) if a.mask == "tracks" else synthetic.mask_random((rows, n), 0.4, 3)
         img = synthetic.zero_unknown(img, mask)
         bpl = 17 if dt == "f64" else 9
         for method in a.methods.split(","):
@@ -65,7 +67,7 @@ def main():
                         continue
                     chunks = [int(c) for c in a.chunks.split(",")] if kernel == "stream" else [0]
                     for ch, sk in [(c, k) for c in chunks for k in ([int(x) for x in a.vecs.split(",")] if (kernel == "stream" and dt == "f64") else [0])]:
-                        p = make_params(n, n, dtype, code, orientation=a.orientation, dt=step, tension=0.3, epsilon=1.0,
+                        p = make_params(rows, n, dtype, code, orientation=a.orientation, dt=step, tension=0.3, epsilon=1.0,
                                         border={"reflect101": C.HMI_BORDER_REFLECT101, "symmetric": C.HMI_BORDER_SYMMETRIC,
                                                 "zero": C.HMI_BORDER_ZERO}[a.border],
                                         kernel=C.KERNELS[kernel], temporal_block=tb)
@@ -79,7 +81,7 @@ def main():
                             nsw = a.sweeps if kernel == "stream" else max(4, a.sweeps // 4)
                             nsw = (nsw // tb) * tb
                             ms = time_sweeps(s, nsw)
-                        g = n * n * nsw / (ms * 1e-3) / 1e9
+                        g = rows * n * nsw / (ms * 1e-3) / 1e9
                         print(("" if a.border == "reflect101" else a.border + " border ") + "%-8s %s %-7s tb=%d chunk=%-4d vec=%d tma=%d  %8.1f GLUPS  %6.1f%% of HBM roofline (%.0f GB/s algorithmic)"
                               % (method, dt, kernel, tb, ch, sk, a.tma, g, 100 * g * bpl / 6550.4, g * bpl), flush=True)
 
