@@ -610,7 +610,7 @@ int stream_cta_slots(const void *kernel, int threads, size_t smem)
 }
 
 void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, double edge_cost,
-                        int *chunk_rows, int *chunk_rows_edge, int fill)
+                        int *chunk_rows, int *chunk_rows_edge, int min_chunk)
 {
     // Wave-aware chunk heights.  Every warp streams (chunk + 2*halo) rows plus a pipeline fill and
     // the launch takes ceil(CTAs / resident CTAs) rounds of that; a fixed chunk height leaves the
@@ -621,7 +621,7 @@ void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int 
     // shorter and are scheduled first; without that a single full wave is slower than three ragged
     // ones, because the whole launch waits for the two edge strips (profiles/r02_tune_skew_ab.log,
     // profiles/r02_tune_tv_chunks.log).
-    // fill = a chunk's fixed cost in rows (pipeline fill, ring prefetch, prologue)
+    const int fill = 8;
     // Load balance.  A launch of r rounds does not take r times one round: all warps of a round start together, the
     // round ends with its slowest warp (edge strips, DRAM page conflicts) and the SMs idle while it drains, so a
     // launch of few long rounds loses to one of a few more, shorter ones although those recompute more overlap rows.
@@ -631,11 +631,12 @@ void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int 
     // drain time per launch reproduces every one of those optima (and leaves many-wave launches alone).
     static double round_bias = -1.0;
     if (round_bias < 0.0) round_bias = getenv("HMI_PICK_ROUND_BIAS") ? atof(getenv("HMI_PICK_ROUND_BIAS")) : 0.5;
-    // (chunks under ~48 rows never pay: with the load-balance term the model would cut a 4096^2 fp32 TV grid into three
-    // rounds of 32-row chunks, measured 4 % slower than one round of 100-row chunks — a chunk's fixed cost is more than
-    // the 2*halo + fill rows counted here, profiles/r05_tune_picker_round_bias_nl_f32.log)
+    // (short chunks never pay — a chunk's fixed cost is more than the 2*halo + fill rows counted here: with the
+    // load-balance term and no floor the model cut a 4096^2 fp32 TV grid into three rounds of 32-row chunks, 4 % slower
+    // than one round of 100-row chunks, and with a 48-row floor into two rounds of 50; the fp32 TV / AMLE kernel, whose
+    // rows are the cheapest, asks for 96.  profiles/r05_tune_picker_round_bias_nl_f32.log, ..._min48_summary.txt)
     int lo = 4 * halo;
-    if (lo < 48) lo = 48;
+    if (lo < min_chunk) lo = min_chunk;
     if (lo > nrows) lo = nrows;
     double best = 1e300;
     int best_ch = nrows, best_che = nrows;

@@ -51,7 +51,7 @@ int stream_halo(int method, int k);                 // ghost rows/columns k fuse
 int stream_auto_chunk_rows(int nrows, int nwin, int halo);      // legacy rule (chunk_rows < 0)
 int stream_cta_slots(const void *kernel, int threads, size_t smem);   // CTAs resident on the GPU at once
 void stream_pick_chunks(int nrows, int nwin, int n_edge, int halo, int wpb, int cta_slots, double edge_cost,
-                        int *chunk_rows, int *chunk_rows_edge, int fill = 8);                  // wave-aware (chunk_rows == 0)
+                        int *chunk_rows, int *chunk_rows_edge, int min_chunk = 48);                  // wave-aware (chunk_rows == 0)
 int stream_max_blocks(int method, int rows_total, int cols);
 int stream_cells_per_lane(int dtype, int vec);       // V of the instantiation launch_stream picks
 constexpr int STREAM_BOX_ROWS = 3;                   // rows per tensor-map box (tma == 2)

@@ -498,11 +498,8 @@ static cudaError_t launch_nl_one(const NLLaunch<T> &l, cudaStream_t st, int *nbl
         a.n_edge = a.nwin >= 2 ? 2 : 1;
         // general path / lean path, instructions per row (SASS): fp32 2.8, fp64 2.0; be generous — the edge
         // strips are 2 of ~70 and come first
-        // (a chunk's fixed cost counts for 24 rows in fp32, whose rows are cheap: with 8 the load-balance term cut a
-        // 4096^2 fp32 grid into two rounds of 50-row chunks, 4 % slower than one round of 100-row chunks,
-        // profiles/r05_tune_picker_round_bias_min48_summary.txt)
         stream_pick_chunks(nrows, a.nwin, a.n_edge, K, WPB, cta_slots, V == 4 ? 3.5 : 2.5, &a.chunk_rows,
-                           &a.chunk_rows_e, V == 4 ? 24 : 8);
+                           &a.chunk_rows_e, V == 4 ? 96 : 48);
         a.nchunks_e = (nrows + a.chunk_rows_e - 1) / a.chunk_rows_e;
     } else {
         a.chunk_rows = l.chunk_rows > 0 ? l.chunk_rows : stream_nl_auto_chunk_rows(nrows, a.nwin);
