@@ -130,6 +130,9 @@ SYMBOLS = {
     "hmi_host_prefault": (ctypes.c_int, [_vp, _sz]),
     "hmi_release_cache": (ctypes.c_int, []),
     "hmi_upload_pipeline_count": (ctypes.c_int64, []),
+    "hmi_debug_band_steps": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
+    "hmi_debug_pick_chunks": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_double, ctypes.c_int32,
+                                             ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "hmi_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, _i64]),
     "hmi_set_term_thres": (ctypes.c_int, [_vp, ctypes.c_double]),
     "hmi_temporal_block": (ctypes.c_int, [_vp]),

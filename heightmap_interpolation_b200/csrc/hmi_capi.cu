@@ -943,9 +943,41 @@ static bool plan_bands(const hmi_solver *s, BandPlan *pl)
     return true;
 }
 
-// The launches of a skewed schedule: every band runs seq[0], seq[1], ... seq[M-1]; launch q reads grid
-// (base + q) & 1 and writes the other one.  issue(d) queues anti-diagonal d (band j runs launch d - j),
-// bottom band first.  Band sums of launches with `norm` are folded on the device in issue order.
+// ---- the order of the launches, as pure functions (tests/test_host_api_cpu.py checks every read-after-write and
+// write-after-read dependence of these orders through hmi_debug_band_steps) ----------------------------------
+// A step = launch q on the contiguous bands [j_lo, j_hi], all of which are at time level q: ONE kernel launch.
+struct BandStep { int q, j_lo, j_hi, final_band; };     // final_band: the band that is final after this step, or -1
+
+// Head start.  landed = 1 ... nb-1: band `landed` is in HBM now — anti-diagonal landed-1, bottom band first, band by
+// band.  landed = nb: the catch-up after the last band — the bands nb-1-q ... nb-1 are all at time level q, so launch q
+// covers them in one whole-wave launch.  Every band ends up having run launches 0 ... nb-1.
+static void band_head_start_steps(int nb, int landed, std::vector<BandStep> &out)
+{
+    if (landed < nb) {
+        const int d = landed - 1;
+        for (int j = d; j >= 0; --j) out.push_back({d - j, j, j, -1});
+    } else {
+        for (int q = 0; q < nb; ++q) out.push_back({q, nb - 1 - q, nb - 1, -1});
+    }
+}
+
+// Drain of M launches per band.  Ramp: launch q covers the bands 0 ... M-1-q (all at time level q, one whole-wave
+// launch), after which band 0 is final; then anti-diagonal after anti-diagonal, bottom band first, band by band: band j
+// is final after diagonal j + M - 1.
+static void band_drain_steps(int nb, int M, std::vector<BandStep> &out)
+{
+    for (int q = 0; q < M; ++q) {
+        const int j_hi = M - 1 - q < nb - 1 ? M - 1 - q : nb - 1;
+        out.push_back({q, 0, j_hi, q == M - 1 ? 0 : -1});
+    }
+    for (int d = M; d <= nb - 1 + M - 1; ++d) {
+        const int j_hi = d < nb - 1 ? d : nb - 1, j_lo = d - (M - 1) > 0 ? d - (M - 1) : 0;
+        for (int j = j_hi; j >= j_lo; --j) out.push_back({d - j, j, j, d - j == M - 1 ? j : -1});
+    }
+}
+
+// Queues the steps: every band runs seq[0], seq[1], ... seq[M-1]; launch q reads grid (base + q) & 1 and writes the
+// other one.  Band sums of launches with `norm` are folded on the device in issue order.
 struct BandSchedule {
     hmi_solver *s;
     const BandPlan &pl;
@@ -954,42 +986,20 @@ struct BandSchedule {
     cudaStream_t st;
     double *acc;
     bool acc_started = false;
-    int last_done = -1;          // bands 0 ... last_done have been issued their final launch
 
-    int issue(int d)
+    int issue(const BandStep &b)
     {
-        const int nb = pl.nb, M = (int)seq.size();
-        const int j_hi = d < nb - 1 ? d : nb - 1, j_lo = d - (M - 1) > 0 ? d - (M - 1) : 0;
-        for (int j = j_hi; j >= j_lo; --j) {
-            const int q = d - j;
-            s->cur = (base + q) & 1;
-            const int rc = run_block(s, seq[q].k, pl.r0[j], pl.r0[j + 1], seq[q].norm, st, false);
-            if (rc != HMI_OK) return rc;
-            if (seq[q].norm) {
-                accumulate_norm_kernel<<<1, 1, 0, st>>>(acc, s->d_result, acc_started ? 0 : 1);
-                acc_started = true;
-                if (cudaGetLastError() != cudaSuccess) return fail(HMI_ERR_CUDA, "norm accumulation launch failed");
-            }
-            if (q == M - 1) last_done = j;
-        }
-        return HMI_OK;
-    }
-    // launch q on the contiguous bands [j_lo, j_hi], which are all at time level q, as ONE launch (full waves)
-    int issue_range(int q, int j_lo, int j_hi)
-    {
-        s->cur = (base + q) & 1;
-        const int rc = run_block(s, seq[q].k, pl.r0[j_lo], pl.r0[j_hi + 1], seq[q].norm, st, false);
+        s->cur = (base + b.q) & 1;
+        const int rc = run_block(s, seq[b.q].k, pl.r0[b.j_lo], pl.r0[b.j_hi + 1], seq[b.q].norm, st, false);
         if (rc != HMI_OK) return rc;
-        if (seq[q].norm) {
+        if (seq[b.q].norm) {
             accumulate_norm_kernel<<<1, 1, 0, st>>>(acc, s->d_result, acc_started ? 0 : 1);
             acc_started = true;
             if (cudaGetLastError() != cudaSuccess) return fail(HMI_ERR_CUDA, "norm accumulation launch failed");
         }
-        if (q == (int)seq.size() - 1 && j_hi > last_done) last_done = j_hi;
         return HMI_OK;
     }
-    int diagonals() const { return pl.nb - 1 + (int)seq.size(); }
-    // after the last diagonal: the current grid, and the folded sums where the result of a check is read
+    // after the last step: the current grid, and the folded sums where the result of a check is read
     int finish(bool with_norm)
     {
         s->cur = (base + (int)seq.size()) & 1;
@@ -1018,6 +1028,7 @@ static int upload_pipelined(hmi_solver *s, const BandPlan &pl, const void *image
     BandSchedule sch{s, pl, {}, 0, st, s->d_result + 8};
     sch.seq.push_back({1, true});                                  // iteration 0
     for (int q = 1; q < nb; ++q) sch.seq.push_back({s->tb, false});
+    std::vector<BandStep> steps;
     cudaError_t e = cudaSuccess;
     for (int b = 0; b < nb && rc == HMI_OK; ++b) {
         const int rows_b = pl.r0[b + 1] - pl.r0[b];
@@ -1037,11 +1048,17 @@ static int upload_pipelined(hmi_solver *s, const BandPlan &pl, const void *image
                 fill_unknown_kernel<float><<<grid, 256, 0, st>>>((float *)gdst, s->pitch, mdst, s->mpitch, rows_b, p.cols, (float)fill_value);
         }
         if ((e = cudaGetLastError()) != cudaSuccess) break;
-        if (b >= 1) rc = sch.issue(b - 1);         // band b has landed: bands b-1 ... 0 advance by one launch
+        if (b >= 1) {                              // band b has landed: bands b-1 ... 0 advance by one launch
+            steps.clear();
+            band_head_start_steps(nb, b, steps);
+            for (size_t i = 0; i < steps.size() && rc == HMI_OK; ++i) rc = sch.issue(steps[i]);
+        }
     }
-    // everything is in HBM: the bands catch up with band 0.  Bands nb-1-q ... nb-1 are all at time level q now,
-    // so launch q runs on them as one whole-wave launch (band launches are partial waves and cost ~1.35x)
-    for (int q = 0; q < nb && rc == HMI_OK && e == cudaSuccess; ++q) rc = sch.issue_range(q, nb - 1 - q, nb - 1);
+    // everything is in HBM: the bands catch up with band 0 in whole-wave launches (band launches are partial waves
+    // and cost ~1.35x their share)
+    steps.clear();
+    band_head_start_steps(nb, nb, steps);
+    for (size_t i = 0; i < steps.size() && rc == HMI_OK && e == cudaSuccess; ++i) rc = sch.issue(steps[i]);
     if (rc == HMI_OK && e == cudaSuccess) rc = sch.finish(true);
     if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
     if (rc != HMI_OK) return rc;
@@ -1108,24 +1125,17 @@ static int drain_pipelined(hmi_solver *s, const BandPlan &pl, long long n, bool 
             cudaStreamSynchronize(cs);
             cudaStreamDestroy(cs);
         });
-    int n_rec = 0;
-    auto publish = [&]() {                         // bands 0 ... last_done are final: tell the downloader
-        for (; rc == HMI_OK && n_rec <= sch.last_done && e == cudaSuccess; ++n_rec) {
-            e = cudaEventRecord(ev[n_rec], st);
-            if (e == cudaSuccess) recorded.store(n_rec + 1, std::memory_order_release);
+    // ramp (band 0 runs ahead, whole-wave launches), then the bands below finish one anti-diagonal after the other
+    // while the copies run; a band that is final is handed to the downloader at once
+    std::vector<BandStep> steps;
+    band_drain_steps(nb, (int)seq.size(), steps);
+    for (size_t i = 0; i < steps.size() && rc == HMI_OK && e == cudaSuccess; ++i) {
+        rc = sch.issue(steps[i]);
+        const int fb = steps[i].final_band;
+        if (rc == HMI_OK && fb >= 0) {             // (bands become final in order 0, 1, 2 ...)
+            e = cudaEventRecord(ev[fb], st);
+            if (e == cudaSuccess) recorded.store(fb + 1, std::memory_order_release);
         }
-    };
-    // ramp: band 0 runs ahead.  Launch q covers the bands 0 ... M-1-q, all at time level q: one whole-wave launch
-    const int M = (int)seq.size();
-    for (int q = 0; q < M && rc == HMI_OK && e == cudaSuccess; ++q) {
-        const int j_hi = M - 1 - q < nb - 1 ? M - 1 - q : nb - 1;
-        rc = sch.issue_range(q, 0, j_hi);
-    }
-    publish();                                     // band 0 is final
-    // the bands below finish one anti-diagonal after the other while the copies run
-    for (int d = M; d < sch.diagonals() && rc == HMI_OK && e == cudaSuccess; ++d) {
-        rc = sch.issue(d);
-        publish();
     }
     if (rc == HMI_OK && e == cudaSuccess) rc = sch.finish(norm);
     if (rc != HMI_OK || e != cudaSuccess) give_up.store(true);
@@ -1379,6 +1389,40 @@ int hmi_mask_grid(hmi_solver *s, uint8_t **mask_dev, size_t *pitch_bytes)
 }
 
 int64_t hmi_upload_pipeline_count(void) { return (int64_t)g_pipelined_uploads.load(); }
+
+int hmi_debug_band_steps(int32_t nb, int32_t m, int32_t phase, int32_t *out, int32_t cap)
+{
+    if (nb < 1 || m < 1 || !out || cap < 0) return fail(HMI_ERR_BAD_ARG, "bad argument");
+    std::vector<BandStep> steps;
+    if (phase == 0) {
+        steps.push_back({-1, 0, 0, -1});                       // band 0 lands
+        for (int b = 1; b < nb; ++b) {
+            steps.push_back({-1, b, b, -1});                   // band b lands ...
+            band_head_start_steps(nb, b, steps);               // ... and the bands above it advance
+        }
+        band_head_start_steps(nb, nb, steps);
+    } else {
+        band_drain_steps(nb, m, steps);
+    }
+    if ((long long)steps.size() > cap) return fail(HMI_ERR_BAD_ARG, "%zu steps do not fit %d", steps.size(), cap);
+    for (size_t i = 0; i < steps.size(); ++i) {
+        out[4 * i + 0] = steps[i].q; out[4 * i + 1] = steps[i].j_lo;
+        out[4 * i + 2] = steps[i].j_hi; out[4 * i + 3] = steps[i].final_band;
+    }
+    return (int)steps.size();
+}
+
+int hmi_debug_pick_chunks(int32_t nrows, int32_t nwin, int32_t n_edge, int32_t halo, int32_t wpb, int32_t cta_slots,
+                          double edge_cost, int32_t min_chunk, int32_t *chunk_rows, int32_t *chunk_rows_edge)
+{
+    if (nrows < 1 || nwin < 1 || wpb < 1 || cta_slots < 1 || !chunk_rows || !chunk_rows_edge)
+        return fail(HMI_ERR_BAD_ARG, "bad argument");
+    int ch = 0, che = 0;
+    hmi::stream_pick_chunks(nrows, nwin, n_edge, halo, wpb, cta_slots, edge_cost, &ch, &che, min_chunk);
+    *chunk_rows = ch;
+    *chunk_rows_edge = che;
+    return HMI_OK;
+}
 
 int hmi_release_cache(void)
 {

@@ -194,6 +194,17 @@ int hmi_inpaint_host(const hmi_params *params, const void *image, const uint8_t 
  * how many one-shot solves of this process took the pipelined route (tests, bench). */
 int64_t hmi_upload_pipeline_count(void);
 
+/* Introspection for the CPU tests (pure host functions, no device needed).
+ * hmi_debug_band_steps: the launch order of the overlapped copies for nb row bands.  phase 0 = upload head start
+ * (every band runs nb launches), phase 1 = download drain of m launches per band.  Writes 4 ints per step —
+ * q, j_lo, j_hi, final: "launch q on the bands j_lo ... j_hi as one kernel launch; afterwards band `final` (or -1)
+ * is final" — and, in phase 0, a step with q = -1 when band j_lo has landed in HBM.  Returns the number of steps.
+ * hmi_debug_pick_chunks: the chunk heights (interior strips, column-edge strips) the wave-aware picker of the
+ * streaming kernels chooses for a launch of nrows x nwin strips. */
+int hmi_debug_band_steps(int32_t nb, int32_t m, int32_t phase, int32_t *out, int32_t cap);
+int hmi_debug_pick_chunks(int32_t nrows, int32_t nwin, int32_t n_edge, int32_t halo, int32_t wpb, int32_t cta_slots,
+                          double edge_cost, int32_t min_chunk, int32_t *chunk_rows, int32_t *chunk_rows_edge);
+
 /* hmi_inpaint_host with the 'zeros' / 'mean' initialiser fused in: after the upload the unknown cells
  * (mask == 0) of the device copy are set to `fill_value`, so the caller can initialise its own host
  * array (the reference does that in place, inpainting/initializer.py:15-18) concurrently with the

@@ -352,3 +352,81 @@ def test_slab_rows_needed_covers_ghosts():
         assert a == (r0 - 24 if rank > 0 else 0) and b == (r1 + 24 if rank < world - 1 else rows)
     # the exchange depth is clamped so that the ghost rows fit inside the neighbouring slab
     assert slab_rows_needed(40, 4, 1, radius=2, exchange_every=12)[2] == 4
+
+
+# ------------------------------------------------------------------ copies overlapped with the solve: launch order
+def _band_steps(nb, m, phase):
+    import ctypes
+    cap = 4 * (nb + m + 2) * (nb + 2)
+    buf = (ctypes.c_int32 * (4 * cap))()
+    n = C.check(C.lib().hmi_debug_band_steps(nb, m, phase, buf, cap))
+    return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+
+
+def _check_band_order(nb, m, steps, all_landed):
+    """Replay a launch order on a model of the two ping-pong grids.  level[j] = launches band j has completed, so
+    its grid (level & 1) holds time level `level` and the other grid still holds time level level - 1.  Launch q of
+    band j reads time level q of bands j-1, j, j+1 (halo rows) and overwrites what band j kept of time level q - 1."""
+    level = [0] * nb
+    landed = [all_landed] * nb
+    finals = []
+    for q, lo, hi, final in steps:
+        if q < 0:                                   # band lo has landed in HBM
+            assert not landed[lo] and (lo == 0 or landed[lo - 1])
+            landed[lo] = True
+            continue
+        assert 0 <= lo <= hi < nb and 0 <= q < m
+        for j in range(lo, hi + 1):
+            assert landed[j] and level[j] == q, (nb, m, q, j, level[j])
+        for nbr in (lo - 1, hi + 1):                # the bands next to the range provide halo rows at time level q
+            if 0 <= nbr < nb:
+                assert landed[nbr], (nb, m, q, nbr)
+                # q: it is at that level; q + 1: it has moved on, but time level q is still in its other grid
+                assert q <= level[nbr] <= q + 1, (nb, m, q, lo, hi, nbr, level[nbr])
+        for j in range(lo, hi + 1):
+            level[j] = q + 1
+        if final >= 0:
+            assert level[final] == m
+            finals.append(final)
+    assert level == [m] * nb and all(landed)
+    return finals
+
+
+def test_overlapped_copies_launch_order_respects_every_dependence():
+    """csrc/hmi_capi.cu band_head_start_steps / band_drain_steps, the orders upload_pipelined and drain_pipelined
+    queue on one stream: no launch reads a time level that is not there yet or not there any more."""
+    for nb in list(range(1, 20)) + [31, 32, 33, 64]:
+        steps = _band_steps(nb, nb, 0)
+        assert _check_band_order(nb, nb, steps, all_landed=False) == []
+        # under the upload every launch is one band; the catch-up is nb whole-range launches
+        assert sum(1 for q, lo, hi, _ in steps if q >= 0 and hi > lo) == max(nb - 1, 0)
+        for m in sorted({1, 2, 3, nb // 2, nb - 1, nb} - {0}):
+            finals = _check_band_order(nb, m, _band_steps(nb, m, 1), all_landed=True)
+            assert finals == list(range(nb)), (nb, m, finals)      # bands become final top to bottom, each once
+
+
+# ------------------------------------------------------------------ wave-aware chunk picker
+def _pick(nrows, nwin, halo, min_chunk=48, n_edge=2, edge_cost=1.7, slots=444, wpb=4):
+    import ctypes
+    a, b = ctypes.c_int32(), ctypes.c_int32()
+    C.check(C.lib().hmi_debug_pick_chunks(nrows, nwin, n_edge, halo, wpb, slots, edge_cost, min_chunk,
+                                          ctypes.byref(a), ctypes.byref(b)))
+    rounds = -(-((n_edge * -(-nrows // b.value) + (nwin - n_edge) * -(-nrows // a.value) + wpb - 1) // wpb) // slots)
+    return a.value, b.value, rounds
+
+
+def test_chunk_picker_reproduces_the_measured_optima():
+    """profiles/r05_tune_picker_min_rounds.log: the number of rounds of resident CTAs (444 on a B200) that measured
+    fastest when it was forced, for the launches the load-balance term was fitted on — and the launches it must leave
+    alone."""
+    assert _pick(4096, 293, 8)[2] == 4               # 4096 x 32768 fp32 slab, harmonic K = 8 / CCST K = 4 (halo 8)
+    assert _pick(512, 631, 8)[2] == 3                # a 512-row band of the overlapped copies, CCST fp64 K = 3
+    assert _pick(4096, 79, 8)[2] == 2                # 4096^2 CCST fp64
+    assert _pick(4096, 631, 8)[2] == 5               # 4096 x 32768 fp64 slab: unchanged
+    ch, che, rounds = _pick(32768, 631, 8)           # the bench workload: many rounds, chunks of a few hundred rows
+    assert 28 <= rounds <= 36 and 300 <= ch <= 450 and che < ch
+    # fp32 TV / AMLE (edge strips 3.5x, chunks of at least 96 rows): 4096^2 stays one round of ~100-row chunks
+    ch, che, rounds = _pick(4096, 35, 2, min_chunk=96, edge_cost=3.5)
+    assert rounds == 1 and 96 <= ch <= 110
+    # tiny launches: one chunk per strip, never taller than the launch
+    assert _pick(20, 3, 6)[0] <= 20 and _pick(7, 1, 2, n_edge=1)[0] <= 8
